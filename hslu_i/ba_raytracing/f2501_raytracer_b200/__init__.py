@@ -1,0 +1,16 @@
+"""B200-native (sm_100a) render core for the per-pixel render loop of
+kije/HSLU_I.BA_RAYTRACING.F2501_raytracer, behind the reference's Scene / Renderer API.
+
+Importing the package does not need a GPU; every compute call goes through the C ABI of
+librt_b200.so (include/rt_api.h) and raises if the library or a CUDA device is missing --
+there is no CPU, PyTorch or oracle fallback on the product path.
+"""
+from . import _lib
+from ._lib import RtError, load
+from .renderer import DeviceScene, ImageBuffer, RaytracerRenderer, RenderConfig
+from .scene import FlatScene, Mesh, Scene, example_scene, material
+
+__all__ = [
+    "DeviceScene", "FlatScene", "ImageBuffer", "Mesh", "RaytracerRenderer", "RenderConfig", "RtError", "Scene",
+    "example_scene", "load", "material",
+]

@@ -1,0 +1,208 @@
+/*
+ * rt_api.h -- C ABI of librt_b200.so, the B200 (sm_100a) render core that replaces the
+ * per-pixel render loop of kije/HSLU_I.BA_RAYTRACING.F2501_raytracer.
+ *
+ * The reference exposes no FFI.  Its seam for this path is the trait method
+ *     fn render(&self, buffer: &ImageBuffer<W,H>, scene: &Scene<Vec3>)
+ *         (reference src/renderer/mod.rs:92-94, implemented at
+ *          src/renderer/raytracer_renderer.rs:1360-1379)
+ * called from src/main.rs:332, examples/semesterbild.rs:333, examples/test_scene.rs:354.
+ * A Rust shim `impl Renderer<W,H,C> for GpuRaytracerRenderer<C>` (bindings/rust/gpu_renderer.rs,
+ * INTEGRATION.md) flattens `&Scene<Vec3>` into the plain structs below and calls these entry
+ * points.  Everything is plain pointers + sizes; no C++/torch types cross the boundary.
+ *
+ * Conventions: every function returns RT_OK (0) or a negative rt_status; nothing aborts or
+ * throws across the boundary; rt_last_error() gives the thread-local message of the last
+ * failure.  Host arrays are borrowed for the duration of the call only.  There is no CPU
+ * fallback: without a CUDA device every compute entry point returns RT_ERR_NO_DEVICE.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARGUMENT = -1,
+    RT_ERR_NO_DEVICE = -2,
+    RT_ERR_CUDA = -3,
+    RT_ERR_OUT_OF_MEMORY = -4,
+    RT_ERR_IO = -5
+} rt_status;
+
+/* ---- scene description (what the Rust shim flattens `Scene<Vec3>` into) ------------------- */
+
+/* Material<f32> + TransmissionProperties<f32> (reference src/raytracing/material.rs:14-94).
+ * `ior`, `opacity`, `boost` are the raw stored fields; `has_opacity` is the SimdOption mask of
+ * `opacity` (0 for TransmissionProperties::none()/default()). */
+typedef struct rt_material {
+    float color[3];
+    float metallic;
+    float shininess;
+    float ior;
+    float opacity;
+    uint32_t has_opacity;
+    float boost;
+} rt_material;
+
+/* TriangleData<Vec3> (reference src/geometry/basic/triangle.rs:22-48): the three vertices and
+ * the stored normal exactly as the reference holds them (the normal may be non-unit for OBJ
+ * faces, src/scene/scene.rs:102-126).  edge1/edge2 are recomputed as v2-v1, v3-v1. */
+typedef struct rt_triangle {
+    float v1[3];
+    float v2[3];
+    float v3[3];
+    float normal[3];
+    uint32_t material; /* index into rt_scene_desc.materials */
+} rt_triangle;
+
+/* SphereData<Vec3> (reference src/geometry/basic/sphere.rs:20-48); r_sq = radius*radius. */
+typedef struct rt_sphere {
+    float center[3];
+    float radius;
+    uint32_t material;
+} rt_sphere;
+
+/* PointLight<Vec3> (reference src/scene/lighting/light.rs:160-181); `color` is the stored
+ * colour, i.e. already passed through maximize_value (src/color.rs:125-131). */
+typedef struct rt_light {
+    float position[3];
+    float color[3];
+    float intensity;
+} rt_light;
+
+/* Primitive order = the reference's iteration order `GeometryCollection::get_all()`
+ * (src/geometry/render_geometry.rs:146-148) with the kind order fixed to spheres, then
+ * triangles; within a kind, insertion order.  Closest-hit ties go to the later primitive
+ * (src/raytracing/raytracer.rs:193-194). */
+typedef struct rt_scene_desc {
+    const rt_triangle *triangles;
+    uint32_t n_triangles;
+    const rt_sphere *spheres;
+    uint32_t n_spheres;
+    const rt_material *materials;
+    uint32_t n_materials;
+    const rt_light *lights;
+    uint32_t n_lights;
+} rt_scene_desc;
+
+/* ---- render configuration (the reference's cfg!() feature switches, made runtime) ---------- */
+
+enum {
+    RT_FLAG_ANTI_ALIASING = 1u << 0,            /* feature anti_aliasing */
+    RT_FLAG_AA_ROTATION_SCALE = 1u << 1,        /* feature anti_aliasing_rotation_scale */
+    RT_FLAG_REFLECTIONS = 1u << 2,              /* feature reflections */
+    RT_FLAG_REFRACTIONS = 1u << 3,              /* feature refractions */
+    RT_FLAG_BACKFACE_CULLING = 1u << 4,         /* feature backface_culling (per-ray term) */
+    RT_FLAG_PACKET_SEMANTICS = 1u << 5,         /* feature simd_render: AA pattern + cloud sharing */
+    RT_FLAG_COUNT_WORK = 1u << 6,               /* run the counter build (untimed; fills rt_stats counts) */
+    RT_FLAG_ZERO_MISSES = 1u << 7               /* write 0 for miss pixels instead of leaving them */
+};
+
+typedef struct rt_config {
+    uint32_t width;                 /* WINDOW_WIDTH  (src/lib.rs:30-60) */
+    uint32_t height;                /* WINDOW_HEIGHT */
+    uint32_t flags;                 /* RT_FLAG_* */
+    uint32_t aa_samples_per_pixel;  /* ANTIALIASING_SAMPLES_PER_PIXEL: 9 or 24 (raytracer_renderer.rs:89-93) */
+    const float *aa_table;          /* ANTIALIASING_SAMPLES: aa_table_len x [f32;2] (raytracer_renderer.rs:105-127) */
+    uint32_t aa_table_len;          /* next_multiple_of(aa_samples_per_pixel, 8) */
+    uint32_t light_multiplicator;   /* POINT_LIGHT_MULTIPLICATOR M: 1/10/19/28 (raytracer_renderer.rs:75-87) */
+    const float *light_clouds;      /* n_light_clouds x M x [f32;3]: first M points of a Poisson3D
+                                       process in [0,R)^3 (light.rs:183-225); NULL when M == 1 */
+    uint32_t n_light_clouds;        /* K; one cloud is chosen per (pixel, light) by rt_cloud_index() */
+    uint32_t reflection_max_depth;  /* RAYTRACE_REFLECTION_MAX_DEPTH 9/13/21 */
+    uint32_t refraction_max_depth;  /* RAYTRACE_REFRACTION_MAX_DEPTH 8/18/21 */
+    uint64_t seed;                  /* keys rt_cloud_index() */
+    /* interleaved row tiles for multi-GPU: this call renders the image rows r with
+       (r / tile_rows) % tile_world == tile_rank.  tile_world <= 1 renders every row. */
+    uint32_t tile_rows;
+    uint32_t tile_rank;
+    uint32_t tile_world;
+    uint32_t reserved;
+} rt_config;
+
+/* Work counters (RT_FLAG_COUNT_WORK) and timings. A "ray" is one closest-hit query
+ * (Raytracer::cast_ray) or one shadow/transmittance query (Raytracer::has_any_intersection). */
+typedef struct rt_stats {
+    double kernel_ms;        /* device time of the render + resolve kernels (CUDA events) */
+    double total_ms;         /* wall time of the call incl. copies */
+    uint64_t closest_rays;
+    uint64_t shadow_rays;
+    uint64_t box_tests;      /* ray vs child-box tests */
+    uint64_t triangle_tests;
+    uint64_t sphere_tests;
+    uint64_t kernel_launches; /* kernels launched by this call */
+} rt_stats;
+
+typedef struct rt_scene rt_scene; /* opaque: device-resident SoA geometry + BVH */
+
+/* ---- entry points -------------------------------------------------------------------------- */
+
+int rt_api_version(void);
+const char *rt_last_error(void);
+
+/* Number of CUDA devices visible (0 without a GPU / driver). Never fails. */
+int rt_device_count(void);
+
+/* Builds the BVH on the host, packs geometry into the device layout and uploads it to CUDA
+ * device `device`.  Replaces nothing in the reference (it has no acceleration structure);
+ * it is the flattening step the shim runs once per `&Scene<Vec3>`. */
+int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene);
+void rt_scene_destroy(rt_scene *scene);
+
+/* Replaces RaytracerRenderer::render (raytracer_renderer.rs:1369-1378).  `out_argb` is the
+ * ImageBuffer storage: width*height u32, row-major, 0xFFRRGGBB for hit pixels, miss pixels
+ * untouched (renderer/mod.rs:116-125) unless RT_FLAG_ZERO_MISSES.  `out_hit_mask` (optional,
+ * width*height bytes) receives 1 where a pixel was written.  With row tiles only this rank's
+ * rows are touched.  Host buffers; copies are inside the call. */
+int rt_render(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask,
+              rt_stats *stats);
+
+/* Same, but the outputs are DEVICE pointers and the work is enqueued on `cuda_stream`
+ * (a cudaStream_t, may be NULL).  With row tiles the output is the rank's COMPACT slab:
+ * local row j holds image row rt_tile_row(cfg, j).  The call returns after enqueueing unless
+ * `stats` is non-NULL (then it synchronises to fill it). */
+int rt_render_device(rt_scene *scene, const rt_config *cfg, void *d_out_argb, void *d_out_hit_mask,
+                     void *cuda_stream, rt_stats *stats);
+
+/* Row-tile bookkeeping shared by every rank. */
+uint32_t rt_tile_local_rows(const rt_config *cfg);              /* rows this rank renders */
+uint32_t rt_tile_row(const rt_config *cfg, uint32_t local_row); /* image row of a local row */
+
+/* Scatter one rank's compact slab (device) into the full frame (device): the step after the
+ * NCCL gather.  `d_slab` holds rt_tile_local_rows rows of width u32 (or u8 when elem_size==1). */
+int rt_scatter_tile_rows(const rt_config *cfg_of_rank, const void *d_slab, void *d_frame,
+                         uint32_t elem_size, void *cuda_stream);
+
+/* Debug/parity entry points: raw queries against the device BVH for arbitrary rays
+ * (host arrays).  rays: n x 6 floats (origin, un-normalised direction).
+ * closest: out_t[n], out_prim[n] (reference primitive index, 0xFFFFFFFF on miss).
+ * shadow:  max_dist[n] in; out[n x 5] = {occluded, opacity, filter r,g,b}. */
+int rt_trace_closest(rt_scene *scene, uint32_t flags, const float *rays, uint32_t n, float *out_t,
+                     uint32_t *out_prim);
+int rt_trace_shadow(rt_scene *scene, uint32_t flags, const float *rays, const float *max_dist,
+                    uint32_t n, float *out);
+
+/* ---- samplers (stand-ins for fast_poisson 1.0.2, seeded; host code) -------------------------- */
+
+/* ANTIALIASING_SAMPLES table: [0,0], 8 x [1,1], then (randomness != 0) the first table_len-1
+ * points of a Bridson Poisson-disk process on [0,1.2)^2 with radius 3/table_len, else [1,1];
+ * truncated to table_len (raytracer_renderer.rs:105-127). */
+int rt_sampler_aa_table(uint64_t seed, uint32_t samples_per_pixel, int randomness, float *out_table,
+                        uint32_t table_len);
+/* n_clouds clouds, each the first M points of a Bridson Poisson-disk process on [0,R)^3,
+ * R = 1.725 + M/20, radius 4/M, M attempts per active point (light.rs:197-206). */
+int rt_sampler_light_clouds(uint64_t seed, uint32_t m, uint32_t n_clouds, float *out_points);
+/* Which cloud a (pixel, light) pair uses; identical in the oracle. */
+uint32_t rt_cloud_index(uint64_t seed, uint32_t x, uint32_t y, uint32_t light, uint32_t n_clouds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */
