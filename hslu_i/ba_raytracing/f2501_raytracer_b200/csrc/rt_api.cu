@@ -1,0 +1,454 @@
+// rt_api.cu -- the C ABI of librt_b200.so (include/rt_api.h): device scene lifetime, render
+// calls, row-tile bookkeeping and the raw-query parity entry points.
+//
+// Replaces RaytracerRenderer::render (reference src/renderer/raytracer_renderer.rs:1360-1379)
+// and the tiling driver Renderer::render_to_buffer[_chunked_inplace] (src/renderer/mod.rs:96-209)
+// behind it.  There is no CPU path: without a CUDA device every compute entry point fails with
+// RT_ERR_NO_DEVICE.
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "rt_bvh.h"
+#include "rt_internal.h"
+#include "rt_kernels.cuh"
+
+using namespace rtd;
+
+#define CU_CHECK(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess) {                                                                           \
+            int _code = (_e == cudaErrorMemoryAllocation) ? RT_ERR_OUT_OF_MEMORY                           \
+                        : (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver) ? RT_ERR_NO_DEVICE \
+                                                                                         : RT_ERR_CUDA;     \
+            return rt_fail(_code, "%s failed: %s", #expr, cudaGetErrorString(_e));                         \
+        }                                                                                                  \
+    } while (0)
+
+struct rt_scene {
+    int device = 0;
+    DScene d{};
+    void *buf_nodes = nullptr, *buf_prims = nullptr, *buf_shade = nullptr, *buf_mats = nullptr, *buf_lights = nullptr;
+    uint32_t n_nodes = 0, n_prims = 0;
+    int sm_count = 0, ctas_per_sm = 0, ctas_per_sm_count = 0;
+    // per-render scratch, grown on demand
+    float4 *samples = nullptr;
+    size_t samples_cap = 0;
+    float *clouds = nullptr;
+    size_t clouds_cap = 0;
+    unsigned int *work_counter = nullptr;
+    unsigned long long *counters = nullptr;
+    uint32_t *slab_argb = nullptr;
+    uint8_t *slab_mask = nullptr;
+    size_t slab_cap = 0, slab_mask_cap = 0;
+    uint32_t *pinned_argb = nullptr;
+    uint8_t *pinned_mask = nullptr;
+    size_t pinned_cap = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static uint32_t local_rows_of(const rt_config *c) {
+    if (c->tile_world <= 1 || c->tile_rows == 0) return c->height;
+    uint32_t rows = 0;
+    uint32_t n_tiles = (c->height + c->tile_rows - 1) / c->tile_rows;
+    for (uint32_t t = c->tile_rank; t < n_tiles; t += c->tile_world) {
+        uint32_t r0 = t * c->tile_rows;
+        rows += (r0 + c->tile_rows <= c->height) ? c->tile_rows : (c->height - r0);
+    }
+    return rows;
+}
+
+static uint32_t image_row_of(const rt_config *c, uint32_t lr) {
+    if (c->tile_world <= 1 || c->tile_rows == 0) return lr;
+    uint32_t t = lr / c->tile_rows, r = lr - t * c->tile_rows;
+    return (t * c->tile_world + c->tile_rank) * c->tile_rows + r;
+}
+
+static int validate_config(const rt_config *c) {
+    if (!c) return rt_fail(RT_ERR_INVALID_ARGUMENT, "null rt_config");
+    if (c->width == 0 || c->height == 0 || c->width > 65536 || c->height > 65536)
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "invalid image size %ux%u", c->width, c->height);
+    if (c->tile_world > 1 && (c->tile_rows == 0 || c->tile_rank >= c->tile_world))
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "invalid row tiling (rows %u, rank %u, world %u)", c->tile_rows, c->tile_rank, c->tile_world);
+    if (c->flags & RT_FLAG_ANTI_ALIASING) {
+        uint32_t S = (c->flags & RT_FLAG_PACKET_SEMANTICS) ? c->aa_table_len : c->aa_samples_per_pixel;
+        if (!c->aa_table || S == 0 || S > (uint32_t)MAX_AA || c->aa_table_len < S)
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "anti-aliasing needs aa_table with 1..%d samples (got %u, table %u)", MAX_AA, S, c->aa_table_len);
+        if ((c->flags & RT_FLAG_PACKET_SEMANTICS) && (S % 8))
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "packet semantics need a multiple of 8 samples (got %u)", S);
+    }
+    if (c->light_multiplicator > 1 && (!c->light_clouds || c->n_light_clouds == 0))
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "light_multiplicator %u needs light_clouds", c->light_multiplicator);
+    if (c->reflection_max_depth > 0xFFFF || c->refraction_max_depth > 0xFFFF || c->reflection_max_depth >= (uint32_t)PATH_STACK - 1 ||
+        c->refraction_max_depth >= (uint32_t)PATH_STACK - 1)
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "bounce depth %u/%u exceeds the path stack (%d)", c->reflection_max_depth, c->refraction_max_depth, PATH_STACK - 2);
+    return RT_OK;
+}
+
+// crate constants (reference src/lib.rs:73-92) and AA offsets
+// (raytracer_renderer.rs:876-916,1021-1138), evaluated in f32 on the host
+static void fill_params(const rt_scene *s, const rt_config *c, RenderParams &p) {
+    memset(&p, 0, sizeof(p));
+    p.sc = s->d;
+    const uint32_t W = c->width, H = c->height;
+    p.width = W;
+    p.height = H;
+    p.flags = c->flags;
+    const float aspect = (float)H / (float)W;
+    const float sw = 1.0f, sh = sw * aspect, sd = (sw + sh) / 2.0f;
+    const float avg = (sw + sh + sd) / 3.0f;
+    p.w2s_w = sw / (float)W;
+    p.w2s_h = sh / (float)H;
+    p.w2s_d = sd / (float)((W + H) / 2);
+    p.focus_x = sw / 2.0f;
+    p.focus_y = sh / 2.0f;
+    p.focus_z = -1.9f * sd;
+    p.eps_d = 1.1920929e-7f * (100.0f * avg);
+    const bool aa = (c->flags & RT_FLAG_ANTI_ALIASING) != 0, packet = (c->flags & RT_FLAG_PACKET_SEMANTICS) != 0;
+    p.S = aa ? (packet ? c->aa_table_len : c->aa_samples_per_pixel) : 1;
+    p.sample_scale = 1.0f / (float)p.S;
+    if (aa) {
+        const bool rot = (c->flags & RT_FLAG_AA_ROTATION_SCALE) != 0;
+        float xr[3] = {1, 0, 0}, yr[3] = {0, 1, 0};
+        if (rot) {
+            float ang = atanf(0.5f), sn = sinf(ang), cs = cosf(ang);
+            // x.mul_add(cos, y * sin), x.mul_add(-sin, y * cos) on the unit vectors
+            xr[0] = fmaf(1.0f, cs, 0.0f * sn); xr[1] = fmaf(0.0f, cs, 1.0f * sn); xr[2] = fmaf(0.0f, cs, 0.0f * sn);
+            yr[0] = fmaf(1.0f, -sn, 0.0f * cs); yr[1] = fmaf(0.0f, -sn, 1.0f * cs); yr[2] = fmaf(0.0f, -sn, 0.0f * cs);
+        }
+        float dirs[8][3];
+        for (int k = 0; k < 3; k++) {
+            float t = -yr[k], l = -xr[k], r = xr[k], b = yr[k];
+            dirs[0][k] = t; dirs[1][k] = l; dirs[2][k] = b; dirs[3][k] = r;
+            dirs[4][k] = t + l; dirs[5][k] = t + r; dirs[6][k] = b + l; dirs[7][k] = b + r;
+        }
+        for (auto &v : dirs) {
+            float m = sqrtf(fmaf(v[0], v[0], fmaf(v[1], v[1], v[2] * v[2])));
+            float inv = 1.0f / m;
+            v[0] *= inv; v[1] *= inv; v[2] *= inv;
+        }
+        const float scale = rot ? (sqrtf(5.0f) / 2.05f) : 0.85f;
+        for (uint32_t i = 0; i < p.S; i++) {
+            float rx = c->aa_table[2 * i] * p.w2s_w * scale;
+            float ry = c->aa_table[2 * i + 1] * p.w2s_h * scale;
+            const float *bias = dirs[packet ? (i % 8) : 0];
+            p.aa_off[2 * i] = rx * bias[0];
+            p.aa_off[2 * i + 1] = ry * bias[1];
+        }
+    }
+    p.M = c->light_multiplicator ? c->light_multiplicator : 1;
+    p.LM = p.M * s->d.n_lights;
+    p.inv_M = 1.0f / (float)p.M;
+    p.K = c->n_light_clouds;
+    p.seed = c->seed;
+    p.refl_depth = c->reflection_max_depth;
+    p.refr_depth = c->refraction_max_depth;
+    p.tile_rows = c->tile_rows;
+    p.tile_rank = c->tile_rank;
+    p.tile_world = c->tile_world;
+    p.local_rows = local_rows_of(c);
+    p.tiles_x = (W + TILE_W - 1) / TILE_W;
+    uint32_t tiles_y = (p.local_rows + TILE_H - 1) / TILE_H;
+    p.n_items = p.tiles_x * tiles_y * (TILE_W * TILE_H) * p.S;
+}
+
+template <typename T>
+static int grow(T *&ptr, size_t &cap, size_t need_bytes) {
+    if (need_bytes <= cap) return RT_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    CU_CHECK(cudaMalloc((void **)&ptr, need_bytes));
+    cap = need_bytes;
+    return RT_OK;
+}
+
+static int upload(void **dst, const std::vector<float> &src) {
+    size_t bytes = std::max<size_t>(src.size() * sizeof(float), 16);
+    CU_CHECK(cudaMalloc(dst, bytes));
+    if (!src.empty()) CU_CHECK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RT_OK;
+}
+
+static int select_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return rt_fail(RT_ERR_NO_DEVICE, "no CUDA device available (%s); librt_b200 has no CPU fallback",
+                       e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return rt_fail(RT_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, n - 1);
+    CU_CHECK(cudaSetDevice(device));
+    return RT_OK;
+}
+
+// enqueue render + resolve on `stream`; slab outputs are device pointers
+static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, uint32_t *d_argb, uint8_t *d_mask, cudaStream_t stream,
+                          uint64_t *launches) {
+    fill_params(s, cfg, p);
+    if (p.LM > 0 && p.M > 1) {
+        size_t bytes = (size_t)cfg->n_light_clouds * p.M * 3 * sizeof(float);
+        int rc = grow(s->clouds, s->clouds_cap, bytes);
+        if (rc) return rc;
+        CU_CHECK(cudaMemcpyAsync(s->clouds, cfg->light_clouds, bytes, cudaMemcpyHostToDevice, stream));
+        p.clouds = s->clouds;
+    }
+    size_t n_samples = (size_t)p.local_rows * p.width * p.S;
+    int rc = grow(s->samples, s->samples_cap, std::max<size_t>(n_samples, 1) * sizeof(float4));
+    if (rc) return rc;
+    p.samples = s->samples;
+    p.work_counter = s->work_counter;
+    p.counters = s->counters;
+    if (p.local_rows == 0) return RT_OK;
+    CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
+    const bool count = (cfg->flags & RT_FLAG_COUNT_WORK) != 0;
+    if (count) CU_CHECK(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), stream));
+    int grid = s->sm_count * (count ? s->ctas_per_sm_count : s->ctas_per_sm);
+    uint32_t warps_needed = (p.n_items + 31) / 32;
+    grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, (warps_needed + CTA_WARPS - 1) / CTA_WARPS));
+    if (count)
+        render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
+    else
+        render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
+    CU_CHECK(cudaGetLastError());
+    uint32_t n_pix = p.local_rows * p.width;
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask);
+    CU_CHECK(cudaGetLastError());
+    if (launches) *launches += 2;
+    return RT_OK;
+}
+
+static int fetch_counters(rt_scene *s, rt_stats *st) {
+    unsigned long long c[8];
+    CU_CHECK(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    st->closest_rays = c[0];
+    st->shadow_rays = c[1];
+    st->box_tests = c[2];
+    st->triangle_tests = c[3];
+    st->sphere_tests = c[4];
+    return RT_OK;
+}
+
+extern "C" {
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene) {
+    if (!out_scene) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null out_scene");
+    *out_scene = nullptr;
+    rtb::FlatScene flat;
+    int rc = rtb::build_flat_scene(desc, flat);
+    if (rc) return rc;
+    rc = select_device(device);
+    if (rc) return rc;
+    rt_scene *s = new (std::nothrow) rt_scene();
+    if (!s) return rt_fail(RT_ERR_OUT_OF_MEMORY, "out of host memory");
+    s->device = device;
+    auto fail = [&](int code) {
+        rt_scene_destroy(s);
+        return code;
+    };
+    if ((rc = upload(&s->buf_nodes, flat.nodes))) return fail(rc);
+    if ((rc = upload(&s->buf_prims, flat.prims))) return fail(rc);
+    if ((rc = upload(&s->buf_shade, flat.shade_n))) return fail(rc);
+    if ((rc = upload(&s->buf_mats, flat.mats))) return fail(rc);
+    if ((rc = upload(&s->buf_lights, flat.lights))) return fail(rc);
+    s->d.nodes = (const float4 *)s->buf_nodes;
+    s->d.prims = (const float4 *)s->buf_prims;
+    s->d.shade_n = (const float4 *)s->buf_shade;
+    s->d.mats = (const float4 *)s->buf_mats;
+    s->d.lights = (const float4 *)s->buf_lights;
+    s->d.n_prims = flat.n_prims;
+    s->d.n_lights = flat.n_lights;
+    s->d.nan_hit_slot = flat.nan_hit_slot;
+    s->d.nan_hit_slot_culled = flat.nan_hit_slot_culled;
+    s->n_nodes = flat.n_nodes;
+    s->n_prims = flat.n_prims;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(rt_fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    s->sm_count = prop.multiProcessorCount;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm, render_kernel<false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm < 1)
+        return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
+        s->ctas_per_sm_count = 1;
+    if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
+        cudaEventCreate(&s->ev1) != cudaSuccess)
+        return fail(rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out_scene = s;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_scene *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->clouds, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
+    if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+uint32_t rt_tile_local_rows(const rt_config *cfg) { return cfg ? local_rows_of(cfg) : 0; }
+uint32_t rt_tile_row(const rt_config *cfg, uint32_t local_row) { return cfg ? image_row_of(cfg, local_row) : 0; }
+
+int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *d_out_hit_mask, void *cuda_stream, rt_stats *stats) {
+    if (!s || !d_out_argb) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_device: null scene or output");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    CU_CHECK(cudaSetDevice(s->device));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    auto t0 = std::chrono::steady_clock::now();
+    RenderParams p;
+    uint64_t launches = 0;
+    if (stats) CU_CHECK(cudaEventRecord(s->ev0, stream));
+    rc = enqueue_render(s, cfg, p, (uint32_t *)d_out_argb, (uint8_t *)d_out_hit_mask, stream, &launches);
+    if (rc) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        CU_CHECK(cudaEventRecord(s->ev1, stream));
+        CU_CHECK(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CU_CHECK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->kernel_ms = ms;
+        stats->kernel_launches = launches;
+        if (cfg->flags & RT_FLAG_COUNT_WORK) {
+            rc = fetch_counters(s, stats);
+            if (rc) return rc;
+        }
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return RT_OK;
+}
+
+int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, rt_stats *stats) {
+    if (!s || !out_argb) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null scene or output");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    CU_CHECK(cudaSetDevice(s->device));
+    auto t0 = std::chrono::steady_clock::now();
+    const uint32_t rows = local_rows_of(cfg);
+    const size_t n_pix = (size_t)rows * cfg->width;
+    if ((rc = grow(s->slab_argb, s->slab_cap, std::max<size_t>(n_pix, 1) * sizeof(uint32_t)))) return rc;
+    if ((rc = grow(s->slab_mask, s->slab_mask_cap, std::max<size_t>(n_pix, 1)))) return rc;
+    if (s->pinned_cap < n_pix) {
+        if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
+        if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
+        s->pinned_argb = nullptr;
+        s->pinned_mask = nullptr;
+        s->pinned_cap = 0;
+        CU_CHECK(cudaMallocHost((void **)&s->pinned_argb, std::max<size_t>(n_pix, 1) * sizeof(uint32_t)));
+        CU_CHECK(cudaMallocHost((void **)&s->pinned_mask, std::max<size_t>(n_pix, 1)));
+        s->pinned_cap = n_pix;
+    }
+    RenderParams p;
+    uint64_t launches = 0;
+    CU_CHECK(cudaEventRecord(s->ev0, s->stream));
+    rc = enqueue_render(s, cfg, p, s->slab_argb, s->slab_mask, s->stream, &launches);
+    if (rc) return rc;
+    CU_CHECK(cudaEventRecord(s->ev1, s->stream));
+    if (n_pix) {
+        CU_CHECK(cudaMemcpyAsync(s->pinned_argb, s->slab_argb, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CU_CHECK(cudaMemcpyAsync(s->pinned_mask, s->slab_mask, n_pix, cudaMemcpyDeviceToHost, s->stream));
+    }
+    CU_CHECK(cudaStreamSynchronize(s->stream));
+    // ImageBuffer semantics (reference src/renderer/mod.rs:116-125): only hit pixels are stored
+    const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
+    for (uint32_t lr = 0; lr < rows; lr++) {
+        const size_t row = image_row_of(cfg, lr);
+        const uint32_t *src = s->pinned_argb + (size_t)lr * cfg->width;
+        const uint8_t *msk = s->pinned_mask + (size_t)lr * cfg->width;
+        uint32_t *dst = out_argb + row * cfg->width;
+        uint8_t *dmask = out_hit_mask ? out_hit_mask + row * cfg->width : nullptr;
+        for (uint32_t x = 0; x < cfg->width; x++) {
+            if (msk[x]) dst[x] = src[x];
+            else if (zero_misses) dst[x] = 0;
+        }
+        if (dmask) memcpy(dmask, msk, cfg->width);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        CU_CHECK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->kernel_ms = ms;
+        stats->kernel_launches = launches;
+        if (cfg->flags & RT_FLAG_COUNT_WORK) {
+            rc = fetch_counters(s, stats);
+            if (rc) return rc;
+        }
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return RT_OK;
+}
+
+int rt_scatter_tile_rows(const rt_config *cfg, const void *d_slab, void *d_frame, uint32_t elem_size, void *cuda_stream) {
+    if (!cfg || !d_slab || !d_frame || (elem_size != 1 && elem_size != 4))
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scatter_tile_rows: bad argument");
+    uint32_t rows = local_rows_of(cfg);
+    if (!rows) return RT_OK;
+    uint32_t row_bytes = cfg->width * elem_size;
+    size_t total = (size_t)row_bytes * rows;
+    scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        (const uint8_t *)d_slab, (uint8_t *)d_frame, row_bytes, rows, cfg->tile_rows, cfg->tile_rank, cfg->tile_world);
+    CU_CHECK(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_trace_closest(rt_scene *s, uint32_t flags, const float *rays, uint32_t n, float *out_t, uint32_t *out_prim) {
+    if (!s || (n && (!rays || !out_t || !out_prim))) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_trace_closest: null argument");
+    if (!n) return RT_OK;
+    CU_CHECK(cudaSetDevice(s->device));
+    float *d_rays = nullptr, *d_t = nullptr;
+    uint32_t *d_prim = nullptr;
+    CU_CHECK(cudaMalloc((void **)&d_rays, (size_t)n * 6 * sizeof(float)));
+    CU_CHECK(cudaMalloc((void **)&d_t, (size_t)n * sizeof(float)));
+    CU_CHECK(cudaMalloc((void **)&d_prim, (size_t)n * sizeof(uint32_t)));
+    CU_CHECK(cudaMemcpy(d_rays, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice));
+    trace_closest_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d, flags, d_rays, n, d_t, d_prim);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaStreamSynchronize(s->stream));
+    CU_CHECK(cudaMemcpy(out_t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(out_prim, d_prim, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(d_rays);
+    cudaFree(d_t);
+    cudaFree(d_prim);
+    return RT_OK;
+}
+
+int rt_trace_shadow(rt_scene *s, uint32_t flags, const float *rays, const float *max_dist, uint32_t n, float *out) {
+    if (!s || (n && (!rays || !max_dist || !out))) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_trace_shadow: null argument");
+    if (!n) return RT_OK;
+    CU_CHECK(cudaSetDevice(s->device));
+    float *d_rays = nullptr, *d_md = nullptr, *d_out = nullptr;
+    CU_CHECK(cudaMalloc((void **)&d_rays, (size_t)n * 6 * sizeof(float)));
+    CU_CHECK(cudaMalloc((void **)&d_md, (size_t)n * sizeof(float)));
+    CU_CHECK(cudaMalloc((void **)&d_out, (size_t)n * 5 * sizeof(float)));
+    CU_CHECK(cudaMemcpy(d_rays, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMemcpy(d_md, max_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    trace_shadow_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d, flags, d_rays, d_md, n, d_out);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaStreamSynchronize(s->stream));
+    CU_CHECK(cudaMemcpy(out, d_out, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(d_rays);
+    cudaFree(d_md);
+    cudaFree(d_out);
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// rt_bvh.cpp -- host BVH build (binned SAH BVH2, collapsed to BVH4, breadth-first node order)
+// and packing of the scene into the float4 device layout described in rt_bvh.h.
+#include "rt_bvh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <queue>
+
+#include "rt_internal.h"
+
+namespace rtb {
+namespace {
+
+const float INF = std::numeric_limits<float>::infinity();
+constexpr float F32_EPS = 1.1920929e-7f;
+
+struct Box {
+    float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
+    void grow(const Box &b) {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], b.lo[k]);
+            hi[k] = std::max(hi[k], b.hi[k]);
+        }
+    }
+    void grow_pt(const float *p) {
+        for (int k = 0; k < 3; k++) {
+            lo[k] = std::min(lo[k], p[k]);
+            hi[k] = std::max(hi[k], p[k]);
+        }
+    }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0) || !(dy >= 0) || !(dz >= 0)) return 0.0f;
+        return 2.0f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct Node2 {
+    Box box;
+    int32_t left = -1, right = -1;  // internal
+    uint32_t first = 0, count = 0;  // leaf (count > 0)
+};
+
+struct Builder {
+    std::vector<Box> pbox;       // padded primitive boxes
+    std::vector<float> centroid; // 3 per primitive
+    std::vector<uint32_t> order;
+    std::vector<Node2> nodes;
+    bool median_only = false;
+
+    int32_t build(uint32_t first, uint32_t count, int depth) {
+        Node2 nd;
+        Box cb;
+        for (uint32_t i = first; i < first + count; i++) {
+            nd.box.grow(pbox[order[i]]);
+            cb.grow_pt(&centroid[3 * order[i]]);
+        }
+        int32_t idx = (int32_t)nodes.size();
+        nodes.push_back(nd);
+        auto make_leaf = [&]() {
+            nodes[idx].first = first;
+            nodes[idx].count = count;
+            return idx;
+        };
+        if (count == 1) return make_leaf();
+        int axis = -1;
+        uint32_t mid = 0;
+        const int NB = 16;
+        const float C_TRAV = 1.0f, C_ISECT = 1.25f;
+        float best = INF;
+        if (!median_only && depth < 28) {
+            float parent_area = nd.box.area();
+            for (int a = 0; a < 3; a++) {
+                float lo = cb.lo[a], ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.0f)) continue;
+                Box bb[NB];
+                uint32_t bc[NB] = {0};
+                float scale = (float)NB / ext;
+                for (uint32_t i = first; i < first + count; i++) {
+                    uint32_t p = order[i];
+                    int b = std::min(NB - 1, std::max(0, (int)((centroid[3 * p + a] - lo) * scale)));
+                    bc[b]++;
+                    bb[b].grow(pbox[p]);
+                }
+                float rarea[NB];
+                uint32_t rcnt[NB];
+                Box acc;
+                uint32_t c = 0;
+                for (int b = NB - 1; b > 0; b--) {
+                    acc.grow(bb[b]);
+                    c += bc[b];
+                    rarea[b] = acc.area();
+                    rcnt[b] = c;
+                }
+                acc = Box();
+                c = 0;
+                for (int b = 0; b < NB - 1; b++) {
+                    acc.grow(bb[b]);
+                    c += bc[b];
+                    if (c == 0 || rcnt[b + 1] == 0) continue;
+                    float cost = C_TRAV + C_ISECT * (acc.area() * (float)c + rarea[b + 1] * (float)rcnt[b + 1]) / std::max(parent_area, 1e-30f);
+                    if (cost < best) {
+                        best = cost;
+                        axis = a;
+                        mid = b + 1;  // bins [0, mid) go left
+                    }
+                }
+            }
+            if (axis >= 0) {
+                if (count <= MAX_LEAF && best >= C_ISECT * (float)count) return make_leaf();
+                float lo = cb.lo[axis], scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
+                uint32_t split_bin = mid;
+                auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
+                    int b = std::min(NB - 1, std::max(0, (int)((centroid[3 * p + axis] - lo) * scale)));
+                    return (uint32_t)b < split_bin;
+                });
+                mid = (uint32_t)(it - order.begin());
+                if (mid == first || mid == first + count) axis = -1;
+            }
+        }
+        if (axis < 0) {
+            if (count <= MAX_LEAF) return make_leaf();
+            // median split along the widest centroid axis (also the fallback that bounds the depth)
+            int a = 0;
+            for (int k = 1; k < 3; k++)
+                if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
+            mid = first + count / 2;
+            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                             [&](uint32_t x, uint32_t y) { return centroid[3 * x + a] < centroid[3 * y + a]; });
+        }
+        int32_t l = build(first, mid - first, depth + 1);
+        int32_t r = build(mid, first + count - mid, depth + 1);
+        nodes[idx].left = l;
+        nodes[idx].right = r;
+        return idx;
+    }
+};
+
+inline float u2f(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+}  // namespace
+
+int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
+    if (!d) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null scene description");
+    if ((d->n_triangles && !d->triangles) || (d->n_spheres && !d->spheres) || (d->n_materials && !d->materials) ||
+        (d->n_lights && !d->lights))
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null array with non-zero count");
+    const uint64_t n64 = (uint64_t)d->n_triangles + d->n_spheres;
+    if (n64 > LEAF_FIRST_MASK) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: too many primitives (%llu)", (unsigned long long)n64);
+    if (d->n_materials > PRIM_MATERIAL_MASK) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: too many materials");
+    const uint32_t n = (uint32_t)n64, ns = d->n_spheres, nt = d->n_triangles;
+    for (uint32_t i = 0; i < ns; i++)
+        if (d->spheres[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "sphere %u: material index out of range", i);
+    for (uint32_t i = 0; i < nt; i++)
+        if (d->triangles[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u: material index out of range", i);
+
+    out = FlatScene();
+    out.n_prims = n;
+    out.n_mats = d->n_materials;
+    out.n_lights = d->n_lights;
+
+    // materials and lights
+    std::vector<uint8_t> transmissive(d->n_materials);
+    out.mats.resize(12 * (size_t)d->n_materials);
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const rt_material &m = d->materials[i];
+        // TransmissionProperties::mask (material.rs:44-50)
+        bool tm = m.has_opacity && !(std::fabs(m.opacity - 0.0f) <= F32_EPS);
+        transmissive[i] = tm;
+        float *o = &out.mats[12 * (size_t)i];
+        o[0] = m.color[0]; o[1] = m.color[1]; o[2] = m.color[2]; o[3] = m.metallic;
+        o[4] = m.shininess; o[5] = m.ior; o[6] = m.opacity; o[7] = m.boost;
+        o[8] = u2f(m.has_opacity ? 1u : 0u); o[9] = u2f(tm ? 1u : 0u); o[10] = 0; o[11] = 0;
+    }
+    out.lights.resize(8 * (size_t)d->n_lights);
+    for (uint32_t i = 0; i < d->n_lights; i++) {
+        const rt_light &l = d->lights[i];
+        float *o = &out.lights[8 * (size_t)i];
+        o[0] = l.position[0]; o[1] = l.position[1]; o[2] = l.position[2]; o[3] = l.intensity;
+        o[4] = l.color[0]; o[5] = l.color[1]; o[6] = l.color[2]; o[7] = 0;
+    }
+
+    // primitive boxes; reference order = spheres, then triangles
+    Builder b;
+    b.pbox.resize(n);
+    b.centroid.resize(3 * (size_t)n);
+    Box scene;
+    for (uint32_t i = 0; i < ns; i++) {
+        const rt_sphere &s = d->spheres[i];
+        float r = std::fabs(s.radius);
+        for (int k = 0; k < 3; k++) {
+            b.pbox[i].lo[k] = s.center[k] - r;
+            b.pbox[i].hi[k] = s.center[k] + r;
+        }
+    }
+    for (uint32_t i = 0; i < nt; i++) {
+        const rt_triangle &t = d->triangles[i];
+        Box &bx = b.pbox[ns + i];
+        bx.grow_pt(t.v1);
+        bx.grow_pt(t.v2);
+        bx.grow_pt(t.v3);
+    }
+    float max_abs = 1.0f;
+    for (uint32_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) {
+            float lo = b.pbox[i].lo[k], hi = b.pbox[i].hi[k];
+            if (!std::isfinite(lo) || !std::isfinite(hi)) return rt_fail(RT_ERR_INVALID_ARGUMENT, "primitive %u has non-finite coordinates", i);
+            max_abs = std::max(max_abs, std::max(std::fabs(lo), std::fabs(hi)));
+            b.centroid[3 * (size_t)i + k] = 0.5f * (lo + hi);
+        }
+    }
+    // Padding: absolute part covers the slab arithmetic (|o| * 2^-24 relative error in t) and the
+    // displacement of hits the float triangle solve accepts just outside the exact triangle;
+    // the relative part scales with the primitive.
+    out.box_pad = 1e-4f * max_abs;
+    for (uint32_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) {
+            float pad = out.box_pad + 1e-3f * (b.pbox[i].hi[k] - b.pbox[i].lo[k]);
+            b.pbox[i].lo[k] -= pad;
+            b.pbox[i].hi[k] += pad;
+        }
+        scene.grow(b.pbox[i]);
+    }
+    for (int k = 0; k < 3; k++) {
+        out.scene_lo[k] = n ? scene.lo[k] : 0.0f;
+        out.scene_hi[k] = n ? scene.hi[k] : 0.0f;
+    }
+
+    // BVH2 -> BVH4, retrying with balanced median splits if the tree is too deep for the device stack
+    const uint32_t MAX_BVH4_DEPTH = 20;  // device stack holds 3 * depth + 1 references (rt_device.cuh)
+    struct Ref4 {
+        int32_t node2;
+        uint32_t depth;
+    };
+    for (int attempt = 0; attempt < 2; attempt++) {
+        b.median_only = attempt == 1;
+        b.order.resize(n);
+        for (uint32_t i = 0; i < n; i++) b.order[i] = i;
+        b.nodes.clear();
+        b.nodes.reserve(2 * (size_t)n + 1);
+        int32_t root = n ? b.build(0, n, 0) : -1;
+
+        out.nodes.clear();
+        out.max_depth = 0;
+        std::queue<Ref4> q;  // breadth-first so the top levels are contiguous at the front
+        auto new_node = [&]() {
+            size_t at = out.nodes.size();
+            out.nodes.resize(at + 32);
+            for (int c = 0; c < 4; c++) {
+                for (int k = 0; k < 3; k++) {
+                    out.nodes[at + 4 * k + c] = INF;         // lo
+                    out.nodes[at + 4 * (3 + k) + c] = -INF;  // hi
+                }
+                out.nodes[at + 24 + c] = u2f(CHILD_EMPTY);
+                out.nodes[at + 28 + c] = 0.0f;
+            }
+            return (uint32_t)(at / 32);
+        };
+        new_node();  // node 0 = root
+        if (root >= 0) q.push({root, 1});
+        uint32_t next_index = 0;
+        // node `next_index` is filled from the queue front; children get indices in push order
+        std::vector<int32_t> kids;
+        uint32_t allocated = 1;
+        while (!q.empty()) {
+            Ref4 cur = q.front();
+            q.pop();
+            uint32_t me = next_index++;
+            out.max_depth = std::max(out.max_depth, cur.depth);
+            kids.clear();
+            const Node2 &n2 = b.nodes[cur.node2];
+            if (n2.count > 0) {
+                kids.push_back(cur.node2);  // root is a leaf: single child
+            } else {
+                kids.push_back(n2.left);
+                kids.push_back(n2.right);
+                while (kids.size() < 4) {
+                    int bi = -1;
+                    float ba = -1.0f;
+                    for (size_t i = 0; i < kids.size(); i++) {
+                        const Node2 &k2 = b.nodes[kids[i]];
+                        if (k2.count == 0 && k2.box.area() > ba) {
+                            ba = k2.box.area();
+                            bi = (int)i;
+                        }
+                    }
+                    if (bi < 0) break;
+                    int32_t victim = kids[bi];
+                    kids[bi] = b.nodes[victim].left;
+                    kids.push_back(b.nodes[victim].right);
+                }
+            }
+            size_t at = 32 * (size_t)me;
+            for (size_t c = 0; c < kids.size(); c++) {
+                const Node2 &k2 = b.nodes[kids[c]];
+                for (int k = 0; k < 3; k++) {
+                    out.nodes[at + 4 * k + c] = k2.box.lo[k];
+                    out.nodes[at + 4 * (3 + k) + c] = k2.box.hi[k];
+                }
+                uint32_t ref;
+                if (k2.count > 0) {
+                    ref = CHILD_LEAF | ((k2.count - 1) << 27) | k2.first;
+                } else {
+                    ref = allocated++;
+                    new_node();
+                    q.push({kids[c], cur.depth + 1});
+                }
+                out.nodes[at + 24 + c] = u2f(ref);
+            }
+        }
+        out.n_nodes = (uint32_t)(out.nodes.size() / 32);
+        if (out.max_depth <= MAX_BVH4_DEPTH) break;
+        if (attempt == 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "BVH depth %u exceeds the traversal stack", out.max_depth);
+    }
+    out.root_ref = 0;
+
+    // primitive records in slot order
+    out.prims.assign(16 * (size_t)n, 0.0f);
+    out.shade_n.assign(4 * (size_t)n, 0.0f);
+    uint32_t best_any = 0xFFFFFFFFu, best_tm = 0xFFFFFFFFu;
+    for (uint32_t slot = 0; slot < n; slot++) {
+        uint32_t p = b.order[slot];
+        float *q = &out.prims[16 * (size_t)slot];
+        if (p < ns) {
+            const rt_sphere &s = d->spheres[p];
+            q[0] = s.center[0]; q[1] = s.center[1]; q[2] = s.center[2];
+            q[3] = s.radius * s.radius;  // SphereData::with_material (sphere.rs:43)
+            q[12] = u2f(p);
+            q[13] = u2f(s.material | PRIM_SPHERE | (transmissive[s.material] ? PRIM_TRANSMISSIVE : 0u));
+        } else {
+            const rt_triangle &t = d->triangles[p - ns];
+            float e1[3], e2[3];
+            for (int k = 0; k < 3; k++) {
+                e1[k] = t.v2[k] - t.v1[k];  // triangle.rs:89-90
+                e2[k] = t.v3[k] - t.v1[k];
+            }
+            // first row of ultraviolet's Mat3::inversed for columns [d, -e1, -e2]: (-e1) x (-e2),
+            // with cross = (y.mul_add(oz, -z*oy), ...); the sign flips cancel exactly.
+            float g[3] = {std::fmaf(e1[1], e2[2], -(e1[2] * e2[1])), std::fmaf(e1[2], e2[0], -(e1[0] * e2[2])),
+                          std::fmaf(e1[0], e2[1], -(e1[1] * e2[0]))};
+            q[0] = t.v1[0]; q[1] = t.v1[1]; q[2] = t.v1[2]; q[3] = e1[0];
+            q[4] = e1[1]; q[5] = e1[2]; q[6] = e2[0]; q[7] = e2[1];
+            q[8] = e2[2]; q[9] = g[0]; q[10] = g[1]; q[11] = g[2];
+            q[12] = u2f(p);
+            q[13] = u2f(t.material | (transmissive[t.material] ? PRIM_TRANSMISSIVE : 0u));
+            float *sn = &out.shade_n[4 * (size_t)slot];
+            sn[0] = t.normal[0]; sn[1] = t.normal[1]; sn[2] = t.normal[2];
+            if (p < best_any) {
+                best_any = p;
+                out.nan_hit_slot = (int32_t)slot;
+            }
+            if (transmissive[t.material] && p < best_tm) {
+                best_tm = p;
+                out.nan_hit_slot_culled = (int32_t)slot;
+            }
+        }
+    }
+    return RT_OK;
+}
+
+}  // namespace rtb

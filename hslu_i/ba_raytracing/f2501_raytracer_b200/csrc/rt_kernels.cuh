@@ -1,0 +1,448 @@
+// rt_kernels.cuh -- the render kernels (sm_100a).
+//
+// render_kernel: persistent warps.  Every lane owns one primary sample at a time and walks that
+// sample's reflection/refraction tree depth-first with a private path stack; lanes refill from a
+// global work counter (warp-aggregated atomicAdd) the moment their tree is finished, so the
+// divergent closest-hit phase always runs with as many live lanes as there is work.  The
+// dominant cost -- L*M shadow/transmittance rays per shading point (reference
+// raytracer_renderer.rs:773-870) -- is NOT done per lane: the live hit records of the warp are
+// compacted into shared memory and the (hit, light copy) pairs are flattened over all 32 lanes,
+// so the shadow traversal runs at full warp occupancy however few lanes still have a live path,
+// and neighbouring lanes trace near-identical rays (same origin, jittered copies of one light).
+// resolve_kernel: sums the samples of a pixel in the reference's order, encodes to 0xFFRRGGBB.
+#pragma once
+#include "rt_device.cuh"
+
+namespace rtd {
+
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int PATH_STACK = 24;   // >= 1 + max(reflection, refraction) depth (21) + slack
+constexpr int MAX_AA = 24;
+constexpr int MAX_SM_LIGHTS = 8; // cloud indices cached in shared memory for up to 8 lights
+constexpr int TILE_W = 8, TILE_H = 4;  // work-item order: 8x4-pixel tiles, samples innermost
+
+struct RenderParams {
+    DScene sc;
+    uint32_t width, height, flags;
+    uint32_t S;            // primary samples per pixel
+    uint32_t M, LM;        // light copies per light, total light copies
+    float inv_M;           // 1 / M as f32 (light.rs:194)
+    float w2s_w, w2s_h, w2s_d;
+    float focus_x, focus_y, focus_z;
+    float eps_d;           // default_epsilon_distance component (vector.rs:697-700)
+    float aa_off[2 * MAX_AA];
+    float sample_scale;    // 1 / S
+    const float *clouds;   // K x M x 3
+    uint32_t K;
+    unsigned long long seed;
+    uint32_t refl_depth, refr_depth;
+    uint32_t tile_rows, tile_rank, tile_world, local_rows;
+    uint32_t tiles_x, n_items;
+    float4 *samples;               // local_rows * width * S : (r, g, b, valid)
+    unsigned int *work_counter;
+    unsigned long long *counters;  // closest, shadow, box, tri, sph
+};
+
+RT_DEV uint32_t cloud_index(unsigned long long seed, uint32_t x, uint32_t y, uint32_t light, uint32_t n) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(x + 1u) +
+                           0xBF58476D1CE4E5B9ull * (unsigned long long)(y + 1u) + 0x94D049BB133111EBull * (unsigned long long)(light + 1u);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(((z >> 32) * (unsigned long long)n) >> 32);
+}
+
+RT_DEV uint32_t tile_image_row(const RenderParams &p, uint32_t local_row) {
+    if (p.tile_world <= 1 || p.tile_rows == 0) return local_row;
+    uint32_t t = local_row / p.tile_rows, r = local_row - t * p.tile_rows;
+    return (t * p.tile_world + p.tile_rank) * p.tile_rows + r;
+}
+
+struct PathRec {  // one pending ray of a sample's reflection/refraction tree (48 B)
+    float4 a;     // origin.xyz, ior
+    float4 b;     // direction.xyz (normalised once; Ray::new normalises again), bits(depth | flags)
+    float4 c;     // weight.rgb, unused
+};
+constexpr uint32_t PATH_REFL_CHILD = 1u << 16;  // whole subtree is scaled by attenuation(t) of its first hit
+
+struct WarpShared {
+    float4 rec[32][3];               // hit records: (P, n.x) (n.yz, v.xy) (v.z, bits mat, bits pixel x, bits pixel y)
+    float res[32][6];                // per pair: diffuse rgb, specular rgb
+    float acc[32][6];                // per hit: running sums in light order
+    uint32_t cloud[32][MAX_SM_LIGHTS];
+};
+
+template <bool COUNT>
+__global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderParams p) {
+    __shared__ WarpShared smem[CTA_WARPS];
+    WarpShared &ws = smem[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const DScene &sc = p.sc;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    const bool refl_on = (p.flags & RT_FLAG_REFLECTIONS) != 0;
+    const bool refr_on = (p.flags & RT_FLAG_REFRACTIONS) != 0;
+    const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
+    Counters cn = {0, 0, 0, 0, 0};
+
+    PathRec stack[PATH_STACK];
+    int sp = 0;
+    bool have_item = false, have_ray = false;
+    uint32_t sample_index = 0, pix_x = 0, pix_y = 0;
+    float3 acc = splat(0.0f);
+    bool sample_valid = false;
+    // current ray
+    float3 ro = splat(0.0f), rd = splat(0.0f), rw = splat(0.0f);
+    float r_ior = AIR_IOR;
+    int r_depth = -1;  // -1 = None
+    bool r_refl_child = false, r_primary = false;
+
+    for (;;) {
+        // ---------------------------------------------------------------- refill
+        if (!have_ray && sp > 0) {
+            PathRec pr = stack[--sp];
+            ro = f3(pr.a.x, pr.a.y, pr.a.z);
+            r_ior = pr.a.w;
+            rd = f3(pr.b.x, pr.b.y, pr.b.z);
+            uint32_t bits = __float_as_uint(pr.b.w);
+            r_depth = (int)(bits & 0xFFFFu);
+            r_refl_child = (bits & PATH_REFL_CHILD) != 0;
+            r_primary = false;
+            rw = f3(pr.c.x, pr.c.y, pr.c.z);
+            have_ray = true;
+        }
+        if (!have_ray && have_item) {  // tree finished: publish the sample
+            p.samples[sample_index] = make_float4(acc.x, acc.y, acc.z, sample_valid ? 1.0f : 0.0f);
+            have_item = false;
+        }
+        {
+            bool need = !have_ray;
+            uint32_t need_mask = __ballot_sync(FULL, need);
+            if (need_mask) {
+                uint32_t base = 0;
+                int leader = __ffs(need_mask) - 1;
+                if ((int)lane == leader) base = atomicAdd(p.work_counter, (unsigned int)__popc(need_mask));
+                base = __shfl_sync(FULL, base, leader);
+                uint32_t item = base + __popc(need_mask & ((1u << lane) - 1u));
+                if (need && item < p.n_items) {
+                    uint32_t pix = item / p.S, s = item - pix * p.S;
+                    uint32_t tile = pix / (TILE_W * TILE_H), within = pix - tile * (TILE_W * TILE_H);
+                    uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                    uint32_t x = tx * TILE_W + (within % TILE_W), ly = ty * TILE_H + (within / TILE_W);
+                    if (x < p.width && ly < p.local_rows) {
+                        pix_x = x;
+                        pix_y = tile_image_row(p, ly);
+                        sample_index = (ly * p.width + x) * p.S + s;
+                        // get_pixel_color / render_pixel_colors (raytracer_renderer.rs:1140-1357)
+                        float cx = (float)pix_x * p.w2s_w, cy = (float)pix_y * p.w2s_h;
+                        float3 dir = f3(cx, cy, 0.0f) - f3(p.focus_x, p.focus_y, p.focus_z);
+                        ro = f3(cx + p.aa_off[2 * s], cy + p.aa_off[2 * s + 1], 0.0f);
+                        rd = dir;
+                        rw = splat(1.0f);
+                        r_ior = AIR_IOR;
+                        r_depth = -1;
+                        r_refl_child = false;
+                        r_primary = true;
+                        acc = splat(0.0f);
+                        sample_valid = false;
+                        have_item = true;
+                        have_ray = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, have_ray)) break;
+
+        // ---------------------------------------------------------------- closest hit (per lane)
+        float3 d = splat(0.0f), P = splat(0.0f), N = splat(0.0f);
+        ClosestHit h;
+        h.slot = -1;
+        h.t = 0.0f;
+        h.meta = 0;
+        h.prim = 0;
+        if (have_ray) {
+            d = normalized3(rd);  // Ray::new_with_mask (ray.rs:52-57)
+            h = trace_closest<COUNT>(sc, ro, d, cull, cn);
+        }
+        const bool hit = have_ray && h.slot >= 0;
+        if (hit) {
+            P = ray_at(ro, d, h.t);
+            if (h.meta & rtb::PRIM_SPHERE) {
+                float4 q0 = __ldg(sc.prims + 4 * (size_t)h.slot);
+                N = normalized3(P - f3(q0.x, q0.y, q0.z));
+            } else {
+                float4 sn = __ldg(sc.shade_n + h.slot);
+                N = f3(sn.x, sn.y, sn.z);
+            }
+            if (r_primary) sample_valid = true;
+        }
+
+        // ---------------------------------------------------------------- cooperative lighting
+        const uint32_t live = __ballot_sync(FULL, hit);
+        const uint32_t n_live = __popc(live);
+        const uint32_t my_slot = __popc(live & ((1u << lane) - 1u));
+        if (hit) {
+            ws.rec[my_slot][0] = make_float4(P.x, P.y, P.z, N.x);
+            ws.rec[my_slot][1] = make_float4(N.y, N.z, d.x, d.y);
+            ws.rec[my_slot][2] = make_float4(d.z, __uint_as_float(h.meta & rtb::PRIM_MATERIAL_MASK), __uint_as_float(pix_x), __uint_as_float(pix_y));
+        }
+        if (lane < n_live) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) ws.acc[lane][c] = 0.0f;
+        }
+        __syncwarp();
+        if (p.M > 1) {  // SceneLightSource::preprocess: one cloud per (pixel, light) (light.rs:183-225)
+            for (uint32_t i = lane; i < n_live * MAX_SM_LIGHTS; i += 32) {
+                uint32_t s = i / MAX_SM_LIGHTS, li = i % MAX_SM_LIGHTS;
+                if (li < sc.n_lights) {
+                    uint32_t x = __float_as_uint(ws.rec[s][2].z), y = __float_as_uint(ws.rec[s][2].w);
+                    ws.cloud[s][li] = cloud_index(p.seed, packet_noaa ? x / 8u : x, y, li, p.K);
+                }
+            }
+            __syncwarp();
+        }
+        const uint32_t total = n_live * p.LM;
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t pair = base + lane;
+            float3 dc = splat(0.0f), spc = splat(0.0f);
+            if (pair < total) {
+                const uint32_t s = pair / p.LM, l = pair - s * p.LM;
+                const float4 r0 = ws.rec[s][0], r1 = ws.rec[s][1], r2 = ws.rec[s][2];
+                const float3 hp = f3(r0.x, r0.y, r0.z), hn = f3(r0.w, r1.x, r1.y), view = f3(r1.z, r1.w, r2.x);
+                const Material m = load_material(sc, __float_as_uint(r2.y));
+                uint32_t li = l, cpy = 0;
+                if (p.M > 1) {
+                    li = l / p.M;
+                    cpy = l - li * p.M;
+                }
+                const float4 l0 = __ldg(sc.lights + 2 * li), l1 = __ldg(sc.lights + 2 * li + 1);
+                float3 lpos = f3(l0.x, l0.y, l0.z);
+                float lint = l0.w;
+                const float3 lcol = f3(l1.x, l1.y, l1.z);
+                if (p.M > 1) {
+                    uint32_t ci = li < MAX_SM_LIGHTS
+                                      ? ws.cloud[s][li]
+                                      : cloud_index(p.seed, packet_noaa ? __float_as_uint(r2.z) / 8u : __float_as_uint(r2.z), __float_as_uint(r2.w), li, p.K);
+                    const float *cp = p.clouds + ((size_t)ci * p.M + cpy) * 3;
+                    float3 rp = f3(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2));
+                    lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
+                    lint = p.inv_M * lint;
+                }
+                // calculate_lighting body (raytracer_renderer.rs:773-870)
+                const float3 l2p = lpos - hp;
+                const float3 ldir = normalized3(l2p);
+                const float3 q = hp + ldir * p.eps_d;
+                const float maxd = mag3(lpos - q);
+                const ShadowResult sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
+                if (!sh.occluded) {
+                    // PointLight::calculate_contribution_at (light.rs:261-299)
+                    const float ldist = mag3(l2p) + EPS;
+                    const float cosi = dot3(l2p, hn) / ldist;
+                    const bool pos = cosi > 0.0f;
+                    const float att = 0.95f * (EPS + ldist + ldist * ldist);
+                    const float sig = (tanhf(att) + 1.0f) / 2.0f;
+                    const float lfc = cosi * lint * sclamp(sig, 0.0f, 1.0f);
+                    const float3 ccolor = pos ? (m.color * lcol) : splat(0.0f);
+                    const float cint = pos ? lfc : 0.0f;
+                    const float3 lcs = ccolor / sh.filter;
+                    const float diffuse = smax(dot3(hn, ldir), 0.0f);
+                    float spec = 0.0f;
+                    const bool has_spec = m.shininess > 0.0f;
+                    if (has_spec) {
+                        float3 rr = reflected3(ldir, hn);
+                        float sd = smax(dot3(normalized3(rr), view), 0.0f);
+                        spec = powf(sd, smax(m.shininess * 512.0f, 1.0f));
+                    }
+                    const float lf = diffuse * cint * sh.opacity;
+                    const float sf = cint * sh.opacity * spec;
+                    if (diffuse > 0.0f) {
+                        dc = m.color * lcs * lf;
+                        if (has_spec) spc = lcol * sf;
+                    }
+                }
+            }
+            ws.res[lane][0] = dc.x; ws.res[lane][1] = dc.y; ws.res[lane][2] = dc.z;
+            ws.res[lane][3] = spc.x; ws.res[lane][4] = spc.y; ws.res[lane][5] = spc.z;
+            __syncwarp();
+            // ordered accumulation: 6 lanes (channels) per hit touched by this batch, each adding
+            // its channel in light order -- the same order as the reference's `for light in lights`
+            {
+                const uint32_t end = min(base + 32u, total);
+                const uint32_t s_first = base / p.LM, s_last = (end - 1) / p.LM;
+                const uint32_t ch = lane % 6u;
+                for (uint32_t s = s_first + lane / 6u; s <= s_last && lane < 30u; s += 5u) {
+                    uint32_t k0 = max(base, s * p.LM), k1 = min(end, (s + 1) * p.LM);
+                    float a = ws.acc[s][ch];
+                    for (uint32_t k = k0; k < k1; k++) a = a + ws.res[k - base][ch];
+                    ws.acc[s][ch] = a;
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---------------------------------------------------------------- combine + spawn (owner lane)
+        if (hit) {
+            const Material m = load_material(sc, h.meta & rtb::PRIM_MATERIAL_MASK);
+            float3 light_color = f3(ws.acc[my_slot][0], ws.acc[my_slot][1], ws.acc[my_slot][2]);
+            float3 specular = f3(ws.acc[my_slot][3], ws.acc[my_slot][4], ws.acc[my_slot][5]);
+            const float3 ambient = (m.color * splat(1.0f)) * 0.08f;
+            float3 direct = ambient + light_color;
+            const float df = attenuation(h.t);
+            direct = direct * df;
+            specular = specular * df;
+            // single_raytrace (raytracer_renderer.rs:147-264), linearised: a reflection child's whole
+            // subtree is scaled by attenuation(child.t) (raytracer_renderer.rs:722-727)
+            const float3 w = r_refl_child ? (rw * df) : rw;
+            const bool is_transmissive = m.transmissive;
+            const float3 local = is_transmissive ? specular : (direct + specular);
+            acc = acc + w * local;
+            const bool is_reflective = (m.metallic > 0.0f) || is_transmissive;
+            const float start_ior = r_ior;
+            if (refl_on && is_reflective) {  // calculate_reflection (raytracer_renderer.rs:526-729)
+                float ct = dot3(d, N);
+                bool inside = ct < 0.0f;
+                float3 inormal = inside ? -N : N;
+                float new_ior = inside ? m.ior : AIR_IOR;
+                float eta = inside ? (new_ior / start_ior) : (start_ior / new_ior);
+                float ci = fabsf(ct);
+                float sin2 = eta * eta * (1.0f - ci * ci);
+                bool tir = sin2 >= 1.0f;
+                bool reflective = (m.metallic > 0.0f) || (is_transmissive && tir);
+                if (reflective) {
+                    float3 rdir = normalized3(reflected3(d, N));
+                    bool none = (fabsf(rdir.x - 0.0f) <= EPS) && (fabsf(rdir.y - 0.0f) <= EPS) && (fabsf(rdir.z - 0.0f) <= EPS);
+                    int next = r_depth < 0 ? (int)p.refl_depth : max(r_depth - 1, 0);
+                    if (!none && next > 0 && sp < PATH_STACK) {
+                        float3 reflectance, tmp;
+                        compute_fresnel(m, inormal, -d, start_ior, reflectance, tmp);
+                        float3 co = P + rdir * p.eps_d;
+                        float3 cw = w * reflectance;
+                        stack[sp].a = make_float4(co.x, co.y, co.z, start_ior);
+                        stack[sp].b = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float((uint32_t)next | PATH_REFL_CHILD));
+                        stack[sp].c = make_float4(cw.x, cw.y, cw.z, 0.0f);
+                        sp++;
+                    }
+                }
+            }
+            if (refr_on && is_transmissive) {  // calculate_refractions (raytracer_renderer.rs:279-524)
+                float ct = dot3(d, N);
+                bool entering = ct <= 0.0f;
+                float3 inormal = entering ? -N : N;
+                float new_ior = entering ? m.ior : AIR_IOR;
+                float eta = entering ? (new_ior / start_ior) : (start_ior / new_ior);
+                float inv_eta = 1.0f / eta;
+                float3 tmp, transmittance;
+                compute_fresnel(m, inormal, d, inv_eta, tmp, transmittance);
+                float3 rdir = normalized3(refracted3(d, -inormal, inv_eta));
+                float op = m.opacity;
+                int step = (op < 0.5f) ? 2 : 1;
+                int factor = (op <= 0.3f) ? 3 : ((op < 0.5f) ? 2 : 1);
+                int next = r_depth < 0 ? (int)p.refr_depth / factor : max(r_depth - step, 0);
+                if (next > 0 && sp < PATH_STACK) {
+                    float boost = m.boost + 1.0f;
+                    float3 co = P + rdir * p.eps_d;
+                    float3 cw = w * (transmittance * boost);
+                    stack[sp].a = make_float4(co.x, co.y, co.z, new_ior);
+                    stack[sp].b = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float((uint32_t)next));
+                    stack[sp].c = make_float4(cw.x, cw.y, cw.z, 0.0f);
+                    sp++;
+                }
+            }
+        }
+        have_ray = false;
+        __syncwarp();
+    }
+
+    if (COUNT) {
+        atomicAdd(p.counters + 0, cn.closest);
+        atomicAdd(p.counters + 1, cn.shadow);
+        atomicAdd(p.counters + 2, cn.box);
+        atomicAdd(p.counters + 3, cn.tri);
+        atomicAdd(p.counters + 4, cn.sph);
+    }
+}
+
+// antialiased_raytrace's reduction (raytracer_renderer.rs:974-1015) + to_output + ChunkView::set.
+// Writes the rank's compact slab: local row j = image row tile_image_row(j).
+__global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_argb, uint8_t *__restrict__ out_mask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = p.local_rows * p.width;
+    if (i >= n) return;
+    const float4 *s = p.samples + (size_t)i * p.S;
+    float3 color;
+    bool any = false;
+    if (!(p.flags & RT_FLAG_ANTI_ALIASING)) {
+        float4 v = s[0];
+        color = f3(v.x, v.y, v.z);
+        any = v.w != 0.0f;
+    } else {
+        const float scale = p.sample_scale;
+        auto term = [&](uint32_t k) {
+            float4 v = s[k];
+            any = any || (v.w != 0.0f);
+            return v.w != 0.0f ? f3(v.x, v.y, v.z) * scale : splat(0.0f);
+        };
+        if (!(p.flags & RT_FLAG_PACKET_SEMANTICS)) {
+            float3 res = splat(0.0f);
+            for (uint32_t k = 1; k < p.S; k++) res = term(k) + res;
+            color = res + term(0);
+        } else {
+            float3 lane[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) {
+                float3 res = splat(0.0f);
+                for (uint32_t q = 1; q < p.S / 8; q++) res = term(8 * q + j) + res;
+                lane[j] = res + term(j);
+            }
+            float3 q0 = lane[0] + lane[4], q1 = lane[1] + lane[5], q2 = lane[2] + lane[6], q3 = lane[3] + lane[7];
+            color = (q0 + q2) + (q1 + q3);
+        }
+    }
+    out_argb[i] = any ? encode_argb(color) : 0u;
+    if (out_mask) out_mask[i] = any ? 1 : 0;
+}
+
+// debug/parity kernels: raw BVH queries for arbitrary rays
+__global__ void trace_closest_kernel(DScene sc, uint32_t flags, const float *__restrict__ rays, uint32_t n, float *out_t, uint32_t *out_prim) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Counters cn = {0, 0, 0, 0, 0};
+    float3 o = f3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+    float3 d = normalized3(f3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+    ClosestHit h = trace_closest<false>(sc, o, d, (flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);
+    out_t[i] = h.slot >= 0 ? h.t : __int_as_float(0x7f800000);
+    out_prim[i] = h.slot >= 0 ? h.prim : 0xFFFFFFFFu;
+}
+
+__global__ void trace_shadow_kernel(DScene sc, uint32_t flags, const float *__restrict__ rays, const float *__restrict__ max_dist, uint32_t n,
+                                    float *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Counters cn = {0, 0, 0, 0, 0};
+    float3 o = f3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
+    float3 d = normalized3(f3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
+    ShadowResult s = trace_shadow<false>(sc, o, d, max_dist[i], (flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);
+    out[5 * i] = s.occluded ? 1.0f : 0.0f;
+    out[5 * i + 1] = s.opacity;
+    out[5 * i + 2] = s.filter.x;
+    out[5 * i + 3] = s.filter.y;
+    out[5 * i + 4] = s.filter.z;
+}
+
+// after the NCCL gather: place one rank's compact slab rows at their image rows
+__global__ void scatter_rows_kernel(const uint8_t *__restrict__ slab, uint8_t *__restrict__ frame, uint32_t row_bytes, uint32_t local_rows,
+                                    uint32_t tile_rows, uint32_t tile_rank, uint32_t tile_world) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // in 4-byte words when row_bytes % 4 == 0, else bytes
+    size_t total = (size_t)row_bytes * local_rows;
+    if (i >= total) return;
+    uint32_t lr = (uint32_t)(i / row_bytes), off = (uint32_t)(i - (size_t)lr * row_bytes);
+    uint32_t row = lr;
+    if (tile_world > 1 && tile_rows) {
+        uint32_t t = lr / tile_rows, r = lr - t * tile_rows;
+        row = (t * tile_world + tile_rank) * tile_rows + r;
+    }
+    frame[(size_t)row * row_bytes + off] = slab[i];
+}
+
+}  // namespace rtd
