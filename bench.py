@@ -1,0 +1,337 @@
+#!/usr/bin/env python3
+"""Benchmark of the render path: rays/s and ms/frame of one frame of a reference scene.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+
+A "step" is one frame of the workload: primary rays, BVH traversal, shadow/transmittance rays,
+bounces, AA accumulation and the ARGB framebuffer write.  Default workload = BASELINE.json's
+target config: semesterbild `high_quality` + `simd_render` (768x640, 16 AA samples, 5 lights x
+19 soft-shadow copies).  With N > 1 (torchrun, one rank per GPU) the frame is split into
+interleaved row tiles and gathered on rank 0 over NCCL; the frame (total work) is fixed, so the
+scaling is "strong".  Rays per frame come from the counter build of the same kernels (untimed).
+
+`--impl reference` times the reference's CPU algorithm (the brute-force C++ oracle, all host
+threads; the Rust crate cannot be built in this image) on a bounded pixel sample of the same
+workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (scene, cargo features, description)
+    "c3": ("semesterbild", "high_quality,simd_render", "semesterbild high_quality+simd_render 768x640 S=16 M=19 (BASELINE configs[2])"),
+    "c3_scalar": ("semesterbild", "high_quality", "semesterbild high_quality scalar path 768x640 S=9 M=19"),
+    "c1": ("main", "default,simd_render", "cargo run --release defaults + simd_render 1140x950 S=16 M=19 depth 13/18 (BASELINE configs[0])"),
+    "c1lite": ("main", "", "main.rs --no-default-features 768x640"),
+    "c2": ("test_scene", "simd_render,backface_culling,medium_resolution", "examples/test_scene 1140x950 (BASELINE configs[1])"),
+    "c4": ("semesterbild", "realistic,high_resolution", "semesterbild realistic high_resolution 1620x1350 depth 9/8 (BASELINE configs[3])"),
+}
+# canonical algorithmic costs
+F_BOX, F_TRI, F_SPH = 22, 45, 22
+B_BOX, B_TRI, B_SPH = 32, 52, 20
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name: str, seed: int):
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import RenderConfig, example_scene
+
+    scene_name, features, desc = WORKLOADS[name]
+    flat = example_scene(scene_name, features).flatten()
+    rc = RenderConfig.from_features(features, seed)
+    return flat, rc, features, desc
+
+
+def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
+    """Brute-force oracle (the reference's linear scan) on a random pixel sample; returns rays, seconds."""
+    from oracle import oracle
+
+    W, H = rc.cfg.width, rc.cfg.height
+    rng = np.random.default_rng(seed)
+    pix = rng.choice(W * H, size=min(n_pixels, W * H), replace=False).astype(np.uint32)
+    desc = flat.desc()
+    t0 = time.perf_counter()
+    _, _, _, cnt = oracle.render(desc, rc.cfg, oracle.BRUTE, threads, pix)
+    dt = time.perf_counter() - t0
+    return cnt["closest_rays"] + cnt["shadow_rays"], dt, len(pix)
+
+
+def cpu_baseline(flat, rc, budget_s: float = 15.0) -> dict:
+    cores = os.cpu_count() or 1
+    rays, dt, n = oracle_sample(flat, rc, 4 * cores, cores)
+    per_pixel = max(dt / max(n, 1), 1e-6)
+    n2 = int(max(4 * cores, min(rc.cfg.width * rc.cfg.height, budget_s / per_pixel)))
+    rays, dt, n = oracle_sample(flat, rc, n2, cores)
+    return {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": f"{n} random pixels of the workload ({rays} rays, {dt:.1f} s), brute-force scalar C++ oracle "
+                      f"(linear scan over all {flat.n_primitives} primitives like the reference), {cores} threads"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flat, rc, features, desc = build_workload(args.workload, args.seed)
+    cores = os.cpu_count() or 1
+    # size one step to ~ (120 s / (K + W)) of CPU work
+    rays, dt, n = oracle_sample(flat, rc, 2 * cores, cores)
+    per_pixel = max(dt / max(n, 1), 1e-6)
+    step_budget = max(2.0, 150.0 / (args.steps + args.warmup))
+    n_step = int(max(2 * cores, min(rc.cfg.width * rc.cfg.height, step_budget / per_pixel)))
+    for i in range(args.warmup):
+        oracle_sample(flat, rc, n_step, cores, seed=100 + i)
+    tot_rays, tot_t = 0, 0.0
+    for i in range(args.steps):
+        rays, dt, n = oracle_sample(flat, rc, n_step, cores, seed=200 + i)
+        tot_rays += rays
+        tot_t += dt
+    value = tot_rays / tot_t
+    frame_pixels = rc.cfg.width * rc.cfg.height
+    line = {
+        "impl": "reference", "metric": "rays_per_second", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
+                   "step": f"{n_step} random pixels of the frame per step ({n_step / frame_pixels:.5f} of a frame)"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_step} random pixels per step, brute-force scalar C++ oracle (the reference's linear scan), {cores} threads; "
+                                   "the Rust reference itself cannot be built in this image (no cargo/rustc, crates not vendored)"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ms_per_frame_extrapolated": 1e3 * (tot_t / args.steps) * frame_pixels / n_step,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tile-rows", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import DeviceScene, RenderConfig
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import _lib as L
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import TiledRenderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: librt_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lib = L.load()
+    flat, rc, features, desc = build_workload(args.workload, args.seed)
+    dev = DeviceScene(flat, device=local_rank)
+    tiled = TiledRenderer(dev, rc, rank, world, args.tile_rows)
+
+    # ---- untimed: work counters of this rank's tiles (counter build of the same kernels)
+    import ctypes as C
+
+    rc_count = RenderConfig(L.Config(), rc.aa_table, rc.light_clouds)
+    C.memmove(C.byref(rc_count.cfg), C.byref(tiled.rc.cfg), C.sizeof(L.Config))
+    rc_count.cfg.flags |= L.FLAG_COUNT_WORK
+    st = dev.render_device(rc_count, tiled.slab.data_ptr(), tiled.mask.data_ptr(), None, want_stats=True)
+    counts = {k: allsum(float(st[k])) for k in ("closest_rays", "shadow_rays", "box_tests", "triangle_tests", "sphere_tests")}
+    rays_per_frame = counts["closest_rays"] + counts["shadow_rays"]
+    flops_alg = counts["box_tests"] * F_BOX + counts["triangle_tests"] * F_TRI + counts["sphere_tests"] * F_SPH
+    bytes_alg = counts["box_tests"] * B_BOX + counts["triangle_tests"] * B_TRI + counts["sphere_tests"] * B_SPH
+
+    fp32_peak = C.c_double(0.0)
+    L.check(lib.rt_measure_fp32_peak(local_rank, C.byref(fp32_peak)))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    # ---- warm-up
+    for _ in range(max(args.warmup, 1) if args.warmup else 0):
+        tiled.step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps; per-step CUDA events on the launching stream, L2 flushed between steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        tiled.render_local()
+        ev[i][1].record()
+        tiled.gather()
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+    step_ms = allmax(step_ms)
+    kern_ms_max = allmax(kern_ms)
+    ms_per_step = step_ms / args.steps
+
+    # ---- end to end through the public host API: host buffers, copies inside the timed region
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import ImageBuffer
+
+    h2d = (rc.light_clouds.nbytes if rc.light_clouds is not None else 0) + 4
+    if world == 1:
+        buf = ImageBuffer(rc.cfg.width, rc.cfg.height)
+        dev.render(rc, buf)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            dev.render(rc, buf)  # H2D sampler tables, kernels, D2H framebuffer + mask, host merge
+        e2e_s = time.perf_counter() - t0
+        d2h = rc.cfg.width * rc.cfg.height * 5
+    else:
+        host = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.int32).pin_memory() if rank == 0 else None
+        host_m = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.uint8).pin_memory() if rank == 0 else None
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tiled.step()
+            if rank == 0:
+                host.copy_(tiled.frame, non_blocking=True)
+                host_m.copy_(tiled.frame_mask, non_blocking=True)
+            torch.cuda.synchronize()
+            barrier()
+        e2e_s = allmax(time.perf_counter() - t0)
+        d2h = rc.cfg.width * rc.cfg.height * 5
+    e2e_ms = 1e3 * e2e_s / args.steps
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        kernel_ms = kern_ms_max / args.steps
+        ach_tflops = flops_alg / world / (kernel_ms * 1e-3) / 1e12  # per GPU, dominant kernel
+        line = {
+            "metric": "rays_per_second", "value": rays_per_frame / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
+                       "primitives": flat.n_primitives, "lights": len(flat.lights), "samples_per_pixel": rc.samples_per_pixel,
+                       "light_copies": rc.cfg.light_multiplicator, "rays_per_frame": int(rays_per_frame),
+                       "closest_rays": int(counts["closest_rays"]), "shadow_rays": int(counts["shadow_rays"]),
+                       "parallelism": f"row tiles of {args.tile_rows} rows interleaved over {world} GPU(s), NCCL gather to rank 0",
+                       "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed},
+            "ms_per_frame": ms_per_step,
+            "e2e": {"value": rays_per_frame / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_frame": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(args.steps * (2 + (0 if world == 1 else 2 * world))),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
+                         "frac": ach_tflops / fp32_peak.value if fp32_peak.value else None, "traffic": None,
+                         "kernel": "render_kernel<false>", "kernel_ms": kernel_ms,
+                         "peak_source": "measured in this run: rt_measure_fp32_peak (register FFMA microbenchmark); MEASURED_PEAKS.json has no FP32 figure",
+                         "algorithmic": f"{F_BOX} flop/box test, {F_TRI} flop/triangle test, {F_SPH} flop/sphere test (SURVEY 8d); "
+                                        f"{int(counts['box_tests'])} box, {int(counts['triangle_tests'])} triangle, {int(counts['sphere_tests'])} sphere tests per frame",
+                         "hbm": {"achieved": bytes_alg / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_alg / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                                 "note": "algorithmic node/primitive bytes; the scene is L1/L2 resident, so this is cache not DRAM traffic"}},
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(flat, rc)
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

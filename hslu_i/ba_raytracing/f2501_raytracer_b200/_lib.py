@@ -89,6 +89,7 @@ def _declare(lib: C.CDLL) -> None:
         "rt_api_version": (i32, []),
         "rt_last_error": (C.c_char_p, []),
         "rt_device_count": (i32, []),
+        "rt_measure_fp32_peak": (i32, [i32, P(C.c_double)]),
         "rt_scene_create": (i32, [P(SceneDesc), i32, P(vp)]),
         "rt_scene_destroy": (None, [vp]),
         "rt_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),

@@ -1,0 +1,87 @@
+"""Multi-GPU frame partition: interleaved row tiles, one process per GPU, NCCL gather.
+
+The reference renders shuffled 48x48 chunks on a rayon pool inside one process
+(src/image_buffer.rs:48-97); pixels are independent, so the frame shards with no data-path
+exchange.  Here image rows are dealt out in tiles of `tile_rows` rows, tile t -> rank t % world
+(interleaved because cost is very non-uniform: glass spheres vs. the black border).  Every rank
+renders its tiles into a compact device slab (rt_render_device); the only collective is the gather
+of the finished slabs to rank 0 over NVLink (torch.distributed / NCCL), after which rank 0 places
+the rows with rt_scatter_tile_rows.  Per-pixel sampler streams are keyed by (seed, x, y, light), so
+the image does not depend on the world size.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib as L
+from .renderer import DeviceScene, RenderConfig
+
+DEFAULT_TILE_ROWS = 2
+
+
+def padded_rows(rc: RenderConfig, tile_rows: int, world: int) -> int:
+    """Rows of the largest slab of any rank (gather buffers are padded to this)."""
+    return max(rc.with_tiles(tile_rows, r, world).local_rows() for r in range(world))
+
+
+class TiledRenderer:
+    """One rank's share of a frame + the gather to rank 0."""
+
+    def __init__(self, scene: DeviceScene, rc: RenderConfig, rank: int, world: int, tile_rows: int = DEFAULT_TILE_ROWS):
+        import torch
+
+        self.torch = torch
+        self.scene, self.rank, self.world, self.tile_rows = scene, rank, world, tile_rows
+        self.rc_full = rc
+        self.rc = rc.with_tiles(tile_rows, rank, world) if world > 1 else rc
+        self.width, self.height = rc.cfg.width, rc.cfg.height
+        self.rows = self.rc.local_rows()
+        self.pad_rows = padded_rows(rc, tile_rows, world) if world > 1 else self.rows
+        dev = torch.device("cuda", scene.device)
+        self.slab = torch.zeros(self.pad_rows * self.width, dtype=torch.int32, device=dev)
+        self.mask = torch.zeros(self.pad_rows * self.width, dtype=torch.uint8, device=dev)
+        self.frame = self.frame_mask = self.gathered = self.gathered_mask = None
+        if rank == 0:
+            self.frame = torch.zeros(self.height * self.width, dtype=torch.int32, device=dev)
+            self.frame_mask = torch.zeros(self.height * self.width, dtype=torch.uint8, device=dev)
+            if world > 1:
+                self.gathered = [torch.zeros_like(self.slab) for _ in range(world)]
+                self.gathered_mask = [torch.zeros_like(self.mask) for _ in range(world)]
+
+    def render_local(self) -> None:
+        """Enqueue this rank's tiles on torch's current stream (no host sync)."""
+        stream = self.torch.cuda.current_stream().cuda_stream
+        self.scene.render_device(self.rc, self.slab.data_ptr(), self.mask.data_ptr(), stream)
+
+    def gather(self, with_mask: bool = True) -> None:
+        """Gather the slabs on rank 0 and place their rows into the full frame."""
+        torch = self.torch
+        lib = L.load()
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            self.frame.copy_(self.slab)
+            if with_mask:
+                self.frame_mask.copy_(self.mask)
+            return
+        import torch.distributed as dist
+
+        dist.gather(self.slab, self.gathered if self.rank == 0 else None, dst=0)
+        if with_mask:
+            dist.gather(self.mask, self.gathered_mask if self.rank == 0 else None, dst=0)
+        if self.rank == 0:
+            for r in range(self.world):
+                cfg_r = self.rc_full.with_tiles(self.tile_rows, r, self.world).cfg
+                L.check(lib.rt_scatter_tile_rows(C.byref(cfg_r), self.gathered[r].data_ptr(), self.frame.data_ptr(), 4, stream))
+                if with_mask:
+                    L.check(lib.rt_scatter_tile_rows(C.byref(cfg_r), self.gathered_mask[r].data_ptr(), self.frame_mask.data_ptr(), 1, stream))
+
+    def step(self) -> None:
+        self.render_local()
+        self.gather()
+
+
+def tile_rows_of_rank(rc: RenderConfig, tile_rows: int, rank: int, world: int) -> list[int]:
+    """Image rows owned by `rank` in slab order (host-side bookkeeping; used by tests)."""
+    lib = L.load()
+    cfg = rc.with_tiles(tile_rows, rank, world).cfg
+    return [lib.rt_tile_row(C.byref(cfg), j) for j in range(lib.rt_tile_local_rows(C.byref(cfg)))]

@@ -150,6 +150,10 @@ const char *rt_last_error(void);
 /* Number of CUDA devices visible (0 without a GPU / driver). Never fails. */
 int rt_device_count(void);
 
+/* Measures the FP32 FMA throughput of `device` (TFLOP/s, 2 flop per FMA) with a register-resident
+ * FFMA microbenchmark; the denominator of the FP32 roofline bench.py reports. */
+int rt_measure_fp32_peak(int device, double *out_tflops);
+
 /* Builds the BVH on the host, packs geometry into the device layout and uploads it to CUDA
  * device `device`.  Replaces nothing in the reference (it has no acceleration structure);
  * it is the flattening step the shim runs once per `&Scene<Vec3>`. */

@@ -1,0 +1,276 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs.  Bar (BASELINE.json north_star): hit/miss mask bit-exact, 8-bit pixels within
++-1 LSB on >= 99.9 % of the pixels; integer results (primitive ids, ray counts) exact."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_LSB = 1          # north_star: +-1 LSB ...
+TOL_FRACTION = 0.999  # ... on >= 99.9 % of the pixels
+
+
+def chan_diff(a, b):
+    d = np.zeros(len(a), np.int32)
+    for sh in (16, 8, 0):
+        d = np.maximum(d, np.abs(((a >> sh) & 255).astype(np.int32) - ((b >> sh) & 255).astype(np.int32)))
+    return d
+
+
+def assert_image_parity(gpu_buf, o_argb, o_mask, pix=None):
+    g_argb, g_mask = gpu_buf.buffer, gpu_buf.hit_mask
+    if pix is not None:
+        g_argb, g_mask, o_argb, o_mask = g_argb[pix], g_mask[pix], o_argb[pix], o_mask[pix]
+    assert np.array_equal(g_mask, o_mask), f"hit mask differs on {(g_mask != o_mask).sum()} pixels"
+    d = chan_diff(g_argb, o_argb)
+    frac = float((d <= TOL_LSB).mean())
+    assert frac >= TOL_FRACTION, f"only {frac:.5f} within {TOL_LSB} LSB (max {d.max()})"
+    return d
+
+
+@pytest.fixture(scope="module")
+def scenes(pkg):
+    cache = {}
+
+    def get(name, features):
+        key = (name, features)
+        if key not in cache:
+            flat = pkg.example_scene(name, features).flatten()
+            cache[key] = (flat, pkg.DeviceScene(flat))
+        return cache[key]
+
+    yield get
+    for _, dev in cache.values():
+        dev.close()
+
+
+def random_rays(rng, n):
+    o = rng.uniform(-0.3, 1.3, (n, 3)).astype(np.float32)
+    tgt = rng.uniform(0.0, 1.0, (n, 3)).astype(np.float32)
+    return np.concatenate([o, tgt - o], 1).astype(np.float32)
+
+
+# ---------------------------------------------------------------- raw BVH queries vs the linear scan
+@pytest.mark.parametrize("scene_name,features,n", [("test_scene", "", 200000), ("main", "", 60000), ("main", "high_quality", 12000)])
+def test_bvh_closest_hit_equals_linear_scan(pkg, oracle_mod, scenes, scene_name, features, n):
+    flat, dev = scenes(scene_name, features)
+    rng = np.random.default_rng(1)
+    rays = random_rays(rng, n)
+    for flags in (0, pkg._lib.FLAG_BACKFACE_CULLING):
+        t_g, p_g = dev.trace_closest(rays, flags)
+        t_o, p_o = oracle_mod.trace_closest(flat.desc(), rays, flags, oracle_mod.BRUTE)
+        assert np.array_equal(p_g, p_o)                                   # same primitive (tie rule included)
+        assert np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))   # bit-identical distance
+        assert (p_o != 0xFFFFFFFF).mean() > 0.3
+
+
+@pytest.mark.parametrize("scene_name,features,n", [("test_scene", "", 200000), ("main", "", 60000)])
+def test_bvh_shadow_query_equals_linear_scan(pkg, oracle_mod, scenes, scene_name, features, n):
+    flat, dev = scenes(scene_name, features)
+    rng = np.random.default_rng(2)
+    rays = random_rays(rng, n)
+    md = rng.uniform(0.05, 2.5, n).astype(np.float32)
+    for flags in (0, pkg._lib.FLAG_BACKFACE_CULLING):
+        s_g = dev.trace_shadow(rays, md, flags)
+        s_o = oracle_mod.trace_shadow(flat.desc(), rays, md, flags, oracle_mod.BRUTE)
+        assert np.array_equal(s_g[:, 0], s_o[:, 0])  # occlusion decision exact
+        free = s_o[:, 0] == 0
+        # opacity / colour filter: same terms, accumulated in traversal order instead of scan order
+        assert np.allclose(s_g[free, 1:], s_o[free, 1:], rtol=0, atol=2e-6)
+        assert 0.05 < (~free).mean() < 0.95
+        assert (s_o[free, 1] < 1).any()  # some rays did cross transmissive primitives
+
+
+def test_coincident_primitives_tie_rule(pkg):
+    s = pkg.Scene()
+    for k in range(6):  # six coincident triangles + a far one: the LAST coincident one must win
+        s.add_triangle([-1, -1, 3], [1, -1, 3], [-1, 1, 3], pkg.material([k / 6, 0, 0]))
+    s.add_triangle([-1, -1, 4], [1, -1, 4], [-1, 1, 4], pkg.material([0, 1, 0]))
+    dev = pkg.DeviceScene(s.flatten())
+    t, prim = dev.trace_closest(np.array([[-0.5, -0.5, 0, 0, 0, 1]], np.float32))
+    assert t[0] == 3.0 and prim[0] == 5
+    dev.close()
+
+
+def test_edge_cases_empty_scene_and_nan_rays(pkg, oracle_mod):
+    empty = pkg.Scene().flatten()
+    dev = pkg.DeviceScene(empty)
+    rc = pkg.RenderConfig.from_features("", 0, width=64, height=48)
+    buf, _ = dev.render(rc)
+    assert not buf.hit_mask.any() and not buf.buffer.any()
+    dev.close()
+    s = pkg.Scene()
+    m = pkg.material([0.5, 0.5, 0.5])
+    s.add_sphere([0, 0, 5], 1.0, m)
+    s.add_triangle([-1, -1, 10], [1, -1, 10], [-1, 1, 10], m)
+    flat = s.flatten()
+    dev = pkg.DeviceScene(flat)
+    ray = np.array([[0, 0, 0, float("nan"), 0, 1], [0, 0, 0, 0, 0, 1]], np.float32)
+    t, prim = dev.trace_closest(ray)
+    assert math.isnan(t[0]) and prim[0] == 1 and t[1] == 4.0 and prim[1] == 0
+    sh = dev.trace_shadow(ray, np.array([100, 100], np.float32))
+    assert list(sh[0]) == [0, 1, 1, 1, 1] and sh[1, 0] == 1
+    dev.close()
+
+
+# ---------------------------------------------------------------- full frames
+def full_frame(pkg, oracle_mod, scenes, scene_name, features, seed=0, stride=1, **kw):
+    flat, dev = scenes(scene_name, features)
+    rc = pkg.RenderConfig.from_features(features, seed, **kw)
+    buf, _ = dev.render(rc)
+    W, H = rc.cfg.width, rc.cfg.height
+    pix = None
+    if stride > 1:
+        ys, xs = np.mgrid[0:H:stride, 0:W:stride]
+        pix = (ys * W + xs).astype(np.uint32).ravel()
+    o_argb, o_mask, _, cnt = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+    d = assert_image_parity(buf, o_argb, o_mask, pix)
+    return flat, dev, rc, buf, cnt, d
+
+
+def test_c2_test_scene_full_frame(pkg, oracle_mod, scenes):
+    """BASELINE configs[1]: examples/test_scene, simd_render + backface_culling, 1140x950 (deterministic)."""
+    feat = "simd_render,backface_culling,medium_resolution"
+    flat, dev, rc, buf, cnt, d = full_frame(pkg, oracle_mod, scenes, "test_scene", feat)
+    assert buf.hit_mask.mean() > 0.99
+    rcc = pkg.RenderConfig.from_features(feat, 0, extra_flags=pkg._lib.FLAG_COUNT_WORK)
+    _, st = dev.render(rcc)
+    assert st["closest_rays"] == cnt["closest_rays"] == 1140 * 950
+    assert st["shadow_rays"] == cnt["shadow_rays"]
+
+
+def test_c1lite_no_features_full_frame(pkg, oracle_mod, scenes):
+    """`--no-default-features`: 768x640, text_lowres.obj, hard shadows, no bounces."""
+    flat, dev, rc, buf, cnt, d = full_frame(pkg, oracle_mod, scenes, "main", "")
+    assert 0.79 < buf.hit_mask.mean() < 0.82
+    assert (d == 0).mean() > 0.999
+    rcc = pkg.RenderConfig.from_features("", 0, extra_flags=pkg._lib.FLAG_COUNT_WORK)
+    _, st = dev.render(rcc)
+    assert (st["closest_rays"], st["shadow_rays"]) == (cnt["closest_rays"], cnt["shadow_rays"])
+
+
+def test_c4_bounces_full_frame_reduced(pkg, oracle_mod, scenes):
+    """realistic (reflections + refractions, depth 9/8) on the semesterbild scene; full frame at 540x450
+    plus the ray counts of the whole bounce tree."""
+    feat = "realistic"
+    flat, dev, rc, buf, cnt, d = full_frame(pkg, oracle_mod, scenes, "main", feat, width=540, height=450)
+    rcc = pkg.RenderConfig.from_features(feat, 0, width=540, height=450, extra_flags=pkg._lib.FLAG_COUNT_WORK)
+    _, st = dev.render(rcc)
+    assert (st["closest_rays"], st["shadow_rays"]) == (cnt["closest_rays"], cnt["shadow_rays"])
+    assert st["closest_rays"] > 2 * 540 * 450  # bounces really happened
+
+
+def test_c4_high_resolution_subsampled(pkg, oracle_mod, scenes):
+    """BASELINE configs[3]: realistic + high_resolution at the full 1620x1350, every 3rd pixel."""
+    full_frame(pkg, oracle_mod, scenes, "semesterbild", "realistic,high_resolution", stride=3)
+
+
+@pytest.mark.parametrize("features,stride", [("high_quality,simd_render", 4), ("high_quality", 5)])
+def test_c3_high_quality_subsampled(pkg, oracle_mod, scenes, features, stride):
+    """BASELINE configs[2], the headline: AA (packet 16 / scalar 9 samples) + 95 soft-shadow rays."""
+    full_frame(pkg, oracle_mod, scenes, "semesterbild", features, seed=3, stride=stride)
+
+
+def test_c1_default_features_subsampled(pkg, oracle_mod, scenes):
+    """BASELINE configs[0]: crate defaults (+ simd_render as in the reference's own render): AA with
+    rotation/randomness, soft shadows, bounces 13/18, scene pre-filter; every 9th pixel."""
+    full_frame(pkg, oracle_mod, scenes, "main", "default,simd_render", seed=1, stride=9)
+
+
+def test_extreme_quality_reduced(pkg, oracle_mod, scenes):
+    """extreme_quality + realistic (24 samples, 140 shadow rays, depth 21/21) at 192x160."""
+    full_frame(pkg, oracle_mod, scenes, "semesterbild", "extreme_quality,realistic,simd_render", seed=2, width=192, height=160, n_light_clouds=512)
+
+
+def test_test_scene_with_everything_on(pkg, oracle_mod, scenes):
+    """test_scene has transmissive + metallic triangles first in order (NaN-ray corner) and a light far outside."""
+    full_frame(pkg, oracle_mod, scenes, "test_scene", "simd_render,backface_culling,realistic,anti_aliasing,soft_shadows,anti_aliasing_rotation_scale,anti_aliasing_randomness",
+               seed=9, width=380, height=316, n_light_clouds=256)
+
+
+# ---------------------------------------------------------------- properties at full size
+def test_render_is_deterministic_and_seed_sensitive(pkg, scenes):
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 11)
+    a, _ = dev.render(rc)
+    b, _ = dev.render(rc)
+    assert np.array_equal(a.buffer, b.buffer) and np.array_equal(a.hit_mask, b.hit_mask)
+    c, _ = dev.render(pkg.RenderConfig.from_features(feat, 12))
+    assert np.array_equal(a.hit_mask, c.hit_mask)      # the mask never depends on the sampler
+    assert not np.array_equal(a.buffer, c.buffer)       # penumbrae do
+
+
+def test_miss_pixels_are_left_untouched(pkg, scenes):
+    flat, dev = scenes("main", "")
+    rc = pkg.RenderConfig.from_features("", 0)
+    buf = pkg.ImageBuffer(rc.cfg.width, rc.cfg.height)
+    buf.buffer[:] = 0x12345678
+    dev.render(rc, buf)
+    miss = buf.hit_mask == 0
+    assert miss.any() and (buf.buffer[miss] == 0x12345678).all()       # renderer/mod.rs:116-125
+    assert ((buf.buffer[~miss] >> 24) == 0xFF).all()
+    rcz = pkg.RenderConfig.from_features("", 0, extra_flags=pkg._lib.FLAG_ZERO_MISSES)
+    dev.render(rcz, buf)
+    assert (buf.buffer[miss] == 0).all()
+
+
+@pytest.mark.parametrize("world,tile_rows", [(2, 2), (4, 8), (8, 3)])
+def test_row_tiles_compose_to_the_full_frame(pkg, scenes, world, tile_rows):
+    """Multi-GPU partition emulated on one GPU: rendering each rank's interleaved row tiles and
+    composing them gives exactly the single-GPU frame (sampler streams are keyed by pixel)."""
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 4, width=384, height=320, n_light_clouds=512)
+    full, _ = dev.render(rc)
+    comp = pkg.ImageBuffer(rc.cfg.width, rc.cfg.height)
+    for r in range(world):
+        dev.render(rc.with_tiles(tile_rows, r, world), comp)
+    assert np.array_equal(comp.buffer, full.buffer) and np.array_equal(comp.hit_mask, full.hit_mask)
+
+
+def test_device_output_and_scatter(pkg, scenes):
+    """rt_render_device into torch memory + rt_scatter_tile_rows == rt_render (host path)."""
+    torch = pytest.importorskip("torch")
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import TiledRenderer
+
+    flat, dev = scenes("main", "")
+    rc = pkg.RenderConfig.from_features("", 0)
+    host, _ = dev.render(pkg.RenderConfig.from_features("", 0, extra_flags=pkg._lib.FLAG_ZERO_MISSES))
+    t = TiledRenderer(dev, rc, 0, 1)
+    t.step()
+    torch.cuda.synchronize()
+    assert np.array_equal(t.frame.cpu().numpy().view(np.uint32), host.buffer)
+    assert np.array_equal(t.frame_mask.cpu().numpy(), host.hit_mask)
+    # world 3 slabs scattered by the product kernel
+    frame = torch.zeros(rc.cfg.width * rc.cfg.height, dtype=torch.int32, device="cuda")
+    lib = pkg._lib.load()
+    for r in range(3):
+        tr = TiledRenderer(dev, rc, r, 3, tile_rows=5)
+        tr.render_local()
+        pkg._lib.check(lib.rt_scatter_tile_rows(C.byref(tr.rc.cfg), tr.slab.data_ptr(), frame.data_ptr(), 4, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32), host.buffer)
+
+
+def test_renderer_api_mirror(pkg, oracle_mod):
+    """RaytracerRenderer(features).render(buffer, scene): the reference's call shape (src/main.rs:327-334)."""
+    scene = pkg.example_scene("test_scene", "backface_culling")
+    r = pkg.RaytracerRenderer("backface_culling", seed=0)
+    buf = pkg.ImageBuffer(768, 640)
+    stats = r.render(buf, scene)
+    assert stats["kernel_launches"] == 2 and stats["kernel_ms"] > 0
+    flat = scene.flatten()
+    o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), r.config.cfg, oracle_mod.BVH)
+    assert_image_parity(buf, o_argb, o_mask)
+    with pytest.raises(ValueError):
+        r.render(pkg.ImageBuffer(100, 100), scene)
+    # C++ mirror of the same call (rth_render)
+    lib = pkg._lib.load()
+    out = np.zeros(768 * 640, np.uint32)
+    mask = np.zeros(768 * 640, np.uint8)
+    pkg._lib.check(lib.rth_render(scene._h, b"backface_culling", 0, 0, pkg._lib.ptr(out), pkg._lib.ptr(mask), None))
+    assert np.array_equal(out, buf.buffer) and np.array_equal(mask, buf.hit_mask)
