@@ -358,7 +358,7 @@ int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *
     int rc = validate_config(cfg);
     if (rc) return rc;
     CU_CHECK(cudaSetDevice(s->device));
-    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : s->stream;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL = the legacy default stream, as the caller asked
     auto t0 = std::chrono::steady_clock::now();
     RenderParams p;
     uint64_t launches = 0;

@@ -68,8 +68,7 @@ constexpr uint32_t PATH_REFL_CHILD = 1u << 16;  // whole subtree is scaled by at
 
 struct WarpShared {
     float4 rec[32][3];               // hit records: (P, n.x) (n.yz, v.xy) (v.z, bits mat, bits pixel x, bits pixel y)
-    float res[32][6];                // per pair: diffuse rgb, specular rgb
-    float acc[32][6];                // per hit: running sums in light order
+    float res[32][6];                // per pair: diffuse rgb, specular rgb (only when fewer than 32 hits are live)
     uint32_t cloud[32][MAX_SM_LIGHTS];
 };
 
@@ -187,10 +186,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
             ws.rec[my_slot][1] = make_float4(N.y, N.z, d.x, d.y);
             ws.rec[my_slot][2] = make_float4(d.z, __uint_as_float(h.meta & rtb::PRIM_MATERIAL_MASK), __uint_as_float(pix_x), __uint_as_float(pix_y));
         }
-        if (lane < n_live) {
-#pragma unroll
-            for (int c = 0; c < 6; c++) ws.acc[lane][c] = 0.0f;
-        }
+        // lane s < n_live accumulates the light sums of hit slot s (in light order, like the
+        // reference's `for light in lights`); when all 32 lanes are live, slot == lane == owner.
+        float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
         __syncwarp();
         if (p.M > 1) {  // SceneLightSource::preprocess: one cloud per (pixel, light) (light.rs:183-225)
             for (uint32_t i = lane; i < n_live * MAX_SM_LIGHTS; i += 32) {
@@ -207,7 +205,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
             const uint32_t pair = base + lane;
             float3 dc = splat(0.0f), spc = splat(0.0f);
             if (pair < total) {
-                const uint32_t s = pair / p.LM, l = pair - s * p.LM;
+                // light-major flattening: a batch holds ONE light copy for (up to) 32 neighbouring hit
+                // points, so the 32 shadow rays converge on the same point and traverse together
+                const uint32_t l = pair / n_live, s = pair - l * n_live;
                 const float4 r0 = ws.rec[s][0], r1 = ws.rec[s][1], r2 = ws.rec[s][2];
                 const float3 hp = f3(r0.x, r0.y, r0.z), hn = f3(r0.w, r1.x, r1.y), view = f3(r1.z, r1.w, r2.x);
                 const Material m = load_material(sc, __float_as_uint(r2.y));
@@ -262,30 +262,36 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
                     }
                 }
             }
-            ws.res[lane][0] = dc.x; ws.res[lane][1] = dc.y; ws.res[lane][2] = dc.z;
-            ws.res[lane][3] = spc.x; ws.res[lane][4] = spc.y; ws.res[lane][5] = spc.z;
-            __syncwarp();
-            // ordered accumulation: 6 lanes (channels) per hit touched by this batch, each adding
-            // its channel in light order -- the same order as the reference's `for light in lights`
-            {
-                const uint32_t end = min(base + 32u, total);
-                const uint32_t s_first = base / p.LM, s_last = (end - 1) / p.LM;
-                const uint32_t ch = lane % 6u;
-                for (uint32_t s = s_first + lane / 6u; s <= s_last && lane < 30u; s += 5u) {
-                    uint32_t k0 = max(base, s * p.LM), k1 = min(end, (s + 1) * p.LM);
-                    float a = ws.acc[s][ch];
-                    for (uint32_t k = k0; k < k1; k++) a = a + ws.res[k - base][ch];
-                    ws.acc[s][ch] = a;
+            if (n_live == 32) {
+                sum_d = sum_d + dc;  // pair (l, s = lane): this lane's own hit, next light in order
+                sum_s = sum_s + spc;
+            } else {
+                ws.res[lane][0] = dc.x; ws.res[lane][1] = dc.y; ws.res[lane][2] = dc.z;
+                ws.res[lane][3] = spc.x; ws.res[lane][4] = spc.y; ws.res[lane][5] = spc.z;
+                __syncwarp();
+                if (lane < n_live) {
+                    // batch entry j holds pair base + j = (light (base + j) / n_live, slot (base + j) % n_live)
+                    const uint32_t j0 = (lane + n_live - base % n_live) % n_live;
+                    for (uint32_t j = j0; j < 32u && base + j < total; j += n_live) {  // increasing light index
+                        sum_d = sum_d + f3(ws.res[j][0], ws.res[j][1], ws.res[j][2]);
+                        sum_s = sum_s + f3(ws.res[j][3], ws.res[j][4], ws.res[j][5]);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+        }
+        // hand the sums of slot `my_slot` (held by lane my_slot) to the lane that owns the hit
+        {
+            const int src = hit ? (int)my_slot : (int)lane;
+            sum_d = f3(__shfl_sync(FULL, sum_d.x, src), __shfl_sync(FULL, sum_d.y, src), __shfl_sync(FULL, sum_d.z, src));
+            sum_s = f3(__shfl_sync(FULL, sum_s.x, src), __shfl_sync(FULL, sum_s.y, src), __shfl_sync(FULL, sum_s.z, src));
         }
 
         // ---------------------------------------------------------------- combine + spawn (owner lane)
         if (hit) {
             const Material m = load_material(sc, h.meta & rtb::PRIM_MATERIAL_MASK);
-            float3 light_color = f3(ws.acc[my_slot][0], ws.acc[my_slot][1], ws.acc[my_slot][2]);
-            float3 specular = f3(ws.acc[my_slot][3], ws.acc[my_slot][4], ws.acc[my_slot][5]);
+            float3 light_color = sum_d;
+            float3 specular = sum_s;
             const float3 ambient = (m.color * splat(1.0f)) * 0.08f;
             float3 direct = ambient + light_color;
             const float df = attenuation(h.t);

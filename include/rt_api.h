@@ -169,7 +169,7 @@ int rt_render(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t
               rt_stats *stats);
 
 /* Same, but the outputs are DEVICE pointers and the work is enqueued on `cuda_stream`
- * (a cudaStream_t, may be NULL).  With row tiles the output is the rank's COMPACT slab:
+ * (a cudaStream_t; NULL is the legacy default stream).  With row tiles the output is the rank's COMPACT slab:
  * local row j holds image row rt_tile_row(cfg, j).  The call returns after enqueueing unless
  * `stats` is non-NULL (then it synchronises to fill it). */
 int rt_render_device(rt_scene *scene, const rt_config *cfg, void *d_out_argb, void *d_out_hit_mask,
