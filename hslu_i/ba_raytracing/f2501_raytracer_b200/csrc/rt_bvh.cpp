@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <queue>
@@ -49,6 +50,8 @@ struct Builder {
     std::vector<uint32_t> order;
     std::vector<Node2> nodes;
     bool median_only = false;
+    float c_isect = 1.25f;
+    uint32_t max_leaf = MAX_LEAF;
 
     int32_t build(uint32_t first, uint32_t count, int depth) {
         Node2 nd;
@@ -68,7 +71,7 @@ struct Builder {
         int axis = -1;
         uint32_t mid = 0;
         const int NB = 16;
-        const float C_TRAV = 1.0f, C_ISECT = 1.25f;
+        const float C_TRAV = 1.0f, C_ISECT = c_isect;
         float best = INF;
         if (!median_only && depth < 28) {
             float parent_area = nd.box.area();
@@ -109,7 +112,7 @@ struct Builder {
                 }
             }
             if (axis >= 0) {
-                if (count <= MAX_LEAF && best >= C_ISECT * (float)count) return make_leaf();
+                if (count <= max_leaf && best >= C_ISECT * (float)count) return make_leaf();
                 float lo = cb.lo[axis], scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
                 uint32_t split_bin = mid;
                 auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
@@ -121,7 +124,7 @@ struct Builder {
             }
         }
         if (axis < 0) {
-            if (count <= MAX_LEAF) return make_leaf();
+            if (count <= max_leaf) return make_leaf();
             // median split along the widest centroid axis (also the fallback that bounds the depth)
             int a = 0;
             for (int k = 1; k < 3; k++)
@@ -161,7 +164,6 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
         if (d->triangles[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u: material index out of range", i);
 
     out = FlatScene();
-    out.n_prims = n;
     out.n_mats = d->n_materials;
     out.n_lights = d->n_lights;
 
@@ -186,50 +188,131 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
         o[4] = l.color[0]; o[5] = l.color[1]; o[6] = l.color[2]; o[7] = 0;
     }
 
-    // primitive boxes; reference order = spheres, then triangles
+    // ---- BVH references. Every primitive gets one reference. Optionally (RT_BVH_SPLIT_DIV=d > 0)
+    // triangles whose longest edge exceeds scene_extent / d are referenced once per cell of a k x k
+    // barycentric subdivision (k*k sub-triangles with tight boxes); the device accepts a hit only
+    // in the reference whose cell contains the hit's (u, v) (rt_device.cuh tri_cell), so each
+    // (ray, triangle) hit is still reported exactly once -- required because shadow queries
+    // accumulate over transmissive hits. OFF by default: on the reference's scenes most shading
+    // points lie ON the large wall/floor triangles, whose shadow rays then cross many cell boxes
+    // (measured on B200, high_quality workload: d = 24 -> 49 box tests per ray instead of 21 and
+    // 98 ms instead of 48 ms per frame; parity unchanged). Kept for scenes with large occluders.
     Builder b;
-    b.pbox.resize(n);
-    b.centroid.resize(3 * (size_t)n);
-    Box scene;
+    if (const char *e = getenv("RT_BVH_CISECT")) b.c_isect = (float)atof(e);   // tuning knobs for experiments
+    if (const char *e = getenv("RT_BVH_MAX_LEAF")) b.max_leaf = std::min<uint32_t>(MAX_LEAF, std::max(1, atoi(e)));
+    float split_div = 0.0f;
+    if (const char *e = getenv("RT_BVH_SPLIT_DIV")) split_div = (float)atof(e);
+    Box exact_scene;
+    float max_abs = 1.0f;
     for (uint32_t i = 0; i < ns; i++) {
         const rt_sphere &s = d->spheres[i];
         float r = std::fabs(s.radius);
         for (int k = 0; k < 3; k++) {
-            b.pbox[i].lo[k] = s.center[k] - r;
-            b.pbox[i].hi[k] = s.center[k] + r;
+            float c[2] = {s.center[k] - r, s.center[k] + r};
+            if (!std::isfinite(c[0]) || !std::isfinite(c[1])) return rt_fail(RT_ERR_INVALID_ARGUMENT, "sphere %u has non-finite coordinates", i);
+            exact_scene.lo[k] = std::min(exact_scene.lo[k], c[0]);
+            exact_scene.hi[k] = std::max(exact_scene.hi[k], c[1]);
         }
     }
     for (uint32_t i = 0; i < nt; i++) {
         const rt_triangle &t = d->triangles[i];
-        Box &bx = b.pbox[ns + i];
-        bx.grow_pt(t.v1);
-        bx.grow_pt(t.v2);
-        bx.grow_pt(t.v3);
-    }
-    float max_abs = 1.0f;
-    for (uint32_t i = 0; i < n; i++) {
-        for (int k = 0; k < 3; k++) {
-            float lo = b.pbox[i].lo[k], hi = b.pbox[i].hi[k];
-            if (!std::isfinite(lo) || !std::isfinite(hi)) return rt_fail(RT_ERR_INVALID_ARGUMENT, "primitive %u has non-finite coordinates", i);
-            max_abs = std::max(max_abs, std::max(std::fabs(lo), std::fabs(hi)));
-            b.centroid[3 * (size_t)i + k] = 0.5f * (lo + hi);
+        for (const float *v : {t.v1, t.v2, t.v3}) {
+            for (int k = 0; k < 3; k++)
+                if (!std::isfinite(v[k])) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u has non-finite coordinates", i);
+            exact_scene.grow_pt(v);
         }
     }
-    // Padding: absolute part covers the slab arithmetic (|o| * 2^-24 relative error in t) and the
-    // displacement of hits the float triangle solve accepts just outside the exact triangle;
-    // the relative part scales with the primitive.
-    out.box_pad = 1e-4f * max_abs;
-    for (uint32_t i = 0; i < n; i++) {
-        for (int k = 0; k < 3; k++) {
-            float pad = out.box_pad + 1e-3f * (b.pbox[i].hi[k] - b.pbox[i].lo[k]);
-            b.pbox[i].lo[k] -= pad;
-            b.pbox[i].hi[k] += pad;
-        }
-        scene.grow(b.pbox[i]);
-    }
+    float max_extent = 0.0f;
     for (int k = 0; k < 3; k++) {
-        out.scene_lo[k] = n ? scene.lo[k] : 0.0f;
-        out.scene_hi[k] = n ? scene.hi[k] : 0.0f;
+        if (n) {
+            max_abs = std::max(max_abs, std::max(std::fabs(exact_scene.lo[k]), std::fabs(exact_scene.hi[k])));
+            max_extent = std::max(max_extent, exact_scene.hi[k] - exact_scene.lo[k]);
+        }
+    }
+    // Padding: the absolute part covers the slab arithmetic (|o| * 2^-24 relative error in t) and the
+    // displacement of hits the float triangle solve accepts just outside the exact triangle; the
+    // relative part scales with the reference's own size (DESIGN.md "Conservative traversal").
+    out.box_pad = 1e-4f * max_abs;
+    std::vector<uint32_t> ref_prim, ref_tag;
+    auto add_ref = [&](uint32_t prim, uint32_t tag, Box bx) {
+        for (int k = 0; k < 3; k++) {
+            float pad = out.box_pad + 1e-3f * (bx.hi[k] - bx.lo[k]);
+            bx.lo[k] -= pad;
+            bx.hi[k] += pad;
+        }
+        ref_prim.push_back(prim);
+        ref_tag.push_back(tag);
+        b.pbox.push_back(bx);
+        for (int k = 0; k < 3; k++) b.centroid.push_back(0.5f * (bx.lo[k] + bx.hi[k]));
+    };
+    for (uint32_t i = 0; i < ns; i++) {
+        const rt_sphere &s = d->spheres[i];
+        float r = std::fabs(s.radius);
+        Box bx;
+        for (int k = 0; k < 3; k++) {
+            bx.lo[k] = s.center[k] - r;
+            bx.hi[k] = s.center[k] + r;
+        }
+        add_ref(i, 0, bx);
+    }
+    const float split_len = (split_div > 0.0f && max_extent > 0.0f) ? max_extent / split_div : INF;
+    for (uint32_t i = 0; i < nt; i++) {
+        const rt_triangle &t = d->triangles[i];
+        double e1[3], e2[3], longest = 0.0;
+        for (int k = 0; k < 3; k++) {
+            e1[k] = (double)t.v2[k] - t.v1[k];
+            e2[k] = (double)t.v3[k] - t.v1[k];
+        }
+        for (int a = 0; a < 3; a++) {  // edge lengths |e1|, |e2|, |e2 - e1|
+            double l2 = 0.0;
+            for (int k = 0; k < 3; k++) {
+                double c = a == 0 ? e1[k] : (a == 1 ? e2[k] : e2[k] - e1[k]);
+                l2 += c * c;
+            }
+            longest = std::max(longest, std::sqrt(l2));
+        }
+        uint32_t kdiv = 1;
+        if (longest > split_len) kdiv = (uint32_t)std::min(32.0, std::ceil(longest / split_len));
+        if (kdiv < 2 || ref_prim.size() + (size_t)kdiv * kdiv > (size_t)LEAF_FIRST_MASK / 2) {
+            Box bx;
+            bx.grow_pt(t.v1);
+            bx.grow_pt(t.v2);
+            bx.grow_pt(t.v3);
+            add_ref(ns + i, 0, bx);
+            continue;
+        }
+        auto corner = [&](uint32_t iu, uint32_t jv, float *outp) {
+            for (int k = 0; k < 3; k++) outp[k] = (float)((double)t.v1[k] + e1[k] * ((double)iu / kdiv) + e2[k] * ((double)jv / kdiv));
+        };
+        for (uint32_t iu = 0; iu < kdiv; iu++) {
+            for (uint32_t jv = 0; iu + jv < kdiv; jv++) {
+                float a[3], bb[3], c[3];
+                Box bx;  // upright cell (iu, jv)
+                corner(iu, jv, a);
+                corner(iu + 1, jv, bb);
+                corner(iu, jv + 1, c);
+                bx.grow_pt(a);
+                bx.grow_pt(bb);
+                bx.grow_pt(c);
+                add_ref(ns + i, TRI_CELL(kdiv, iu, jv, 0), bx);
+                if (iu + jv + 2 <= kdiv) {  // inverted cell sharing the same (iu, jv) square
+                    Box by;
+                    corner(iu + 1, jv + 1, a);
+                    by.grow_pt(a);
+                    by.grow_pt(bb);
+                    by.grow_pt(c);
+                    add_ref(ns + i, TRI_CELL(kdiv, iu, jv, 1), by);
+                }
+            }
+        }
+    }
+    const uint32_t n_refs = (uint32_t)ref_prim.size();
+    out.n_prims = n_refs;  // slots = references
+    Box scene;
+    for (uint32_t i = 0; i < n_refs; i++) scene.grow(b.pbox[i]);
+    for (int k = 0; k < 3; k++) {
+        out.scene_lo[k] = n_refs ? scene.lo[k] : 0.0f;
+        out.scene_hi[k] = n_refs ? scene.hi[k] : 0.0f;
     }
 
     // BVH2 -> BVH4, retrying with balanced median splits if the tree is too deep for the device stack
@@ -240,11 +323,11 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     };
     for (int attempt = 0; attempt < 2; attempt++) {
         b.median_only = attempt == 1;
-        b.order.resize(n);
-        for (uint32_t i = 0; i < n; i++) b.order[i] = i;
+        b.order.resize(n_refs);
+        for (uint32_t i = 0; i < n_refs; i++) b.order[i] = i;
         b.nodes.clear();
-        b.nodes.reserve(2 * (size_t)n + 1);
-        int32_t root = n ? b.build(0, n, 0) : -1;
+        b.nodes.reserve(2 * (size_t)n_refs + 1);
+        int32_t root = n_refs ? b.build(0, n_refs, 0) : -1;
 
         out.nodes.clear();
         out.max_depth = 0;
@@ -321,11 +404,11 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     out.root_ref = 0;
 
     // primitive records in slot order
-    out.prims.assign(16 * (size_t)n, 0.0f);
-    out.shade_n.assign(4 * (size_t)n, 0.0f);
+    out.prims.assign(16 * (size_t)n_refs, 0.0f);
+    out.shade_n.assign(4 * (size_t)n_refs, 0.0f);
     uint32_t best_any = 0xFFFFFFFFu, best_tm = 0xFFFFFFFFu;
-    for (uint32_t slot = 0; slot < n; slot++) {
-        uint32_t p = b.order[slot];
+    for (uint32_t slot = 0; slot < n_refs; slot++) {
+        uint32_t p = ref_prim[b.order[slot]];
         float *q = &out.prims[16 * (size_t)slot];
         if (p < ns) {
             const rt_sphere &s = d->spheres[p];
@@ -349,6 +432,7 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
             q[8] = e2[2]; q[9] = g[0]; q[10] = g[1]; q[11] = g[2];
             q[12] = u2f(p);
             q[13] = u2f(t.material | (transmissive[t.material] ? PRIM_TRANSMISSIVE : 0u));
+            q[14] = u2f(ref_tag[b.order[slot]]);
             float *sn = &out.shade_n[4 * (size_t)slot];
             sn[0] = t.normal[0]; sn[1] = t.normal[1]; sn[2] = t.normal[2];
             if (p < best_any) {

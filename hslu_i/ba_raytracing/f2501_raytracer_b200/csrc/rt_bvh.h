@@ -20,13 +20,20 @@ namespace rtb {
 //             q2 = (e2.z, g.x, g.y, g.z)  with g = cross(e1, e2) (the first row of the inverse,
 //                  identical bit for bit to cross(-e1, -e2) evaluated per ray)
 //   sphere:   q0 = (c.x, c.y, c.z, r*r)      q1, q2 unused
-//   both:     q3 = (bits(prim_index), bits(meta), 0, 0)
+//   both:     q3 = (bits(prim_index), bits(meta), bits(cell), 0)
 //             meta = material index | PRIM_TRANSMISSIVE | PRIM_SPHERE
+//             cell = 0, or TRI_CELL(k, i, j, upper) when the slot is one cell of a large triangle
+//                    that is referenced once per cell of a k x k barycentric subdivision
 // prim_index is the reference iteration order (spheres first, then triangles): closest-hit ties go
 // to the larger index (raytracer.rs:193-194).
 constexpr uint32_t PRIM_MATERIAL_MASK = 0x00FFFFFFu;
 constexpr uint32_t PRIM_TRANSMISSIVE = 1u << 30;
 constexpr uint32_t PRIM_SPHERE = 1u << 31;
+// cell tag: k in bits 0..6 (2..32), i in 8..14, j in 16..22, upper (inverted sub-triangle) in bit 24
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr uint32_t TRI_CELL(uint32_t k, uint32_t i, uint32_t j, uint32_t upper) { return k | (i << 8) | (j << 16) | (upper << 24); }
 
 // BVH4 node, 128 B = 8 x float4:
 //   n0..n5 = lo.x, lo.y, lo.z, hi.x, hi.y, hi.z of the four children (SoA: .x = child 0 ...)
@@ -45,7 +52,7 @@ struct FlatScene {
     std::vector<float> shade_n;  // 4 floats per slot: stored triangle normal (spheres: 0)
     std::vector<float> mats;     // 12 floats per material: (color, metallic) (shininess, ior, opacity, boost) (bits has_opacity, bits transmissive, 0, 0)
     std::vector<float> lights;   // 8 floats per light: (pos, intensity) (color, 0)
-    uint32_t n_nodes = 0, n_prims = 0, n_mats = 0, n_lights = 0;
+    uint32_t n_nodes = 0, n_prims = 0, n_mats = 0, n_lights = 0;  // n_prims counts slots (references)
     uint32_t root_ref = CHILD_EMPTY;  // child reference of the root (a leaf ref for tiny scenes)
     // what a ray with a NaN direction "hits" in the reference (every triangle test passes with
     // t = NaN, so the linear scan keeps the first eligible triangle): slot of the lowest-index

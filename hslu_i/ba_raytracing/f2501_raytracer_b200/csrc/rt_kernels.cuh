@@ -235,30 +235,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
                 const float3 q = hp + ldir * p.eps_d;
                 const float maxd = mag3(lpos - q);
                 const ShadowResult sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
-                if (!sh.occluded) {
+                // Everything below only matters when the light is unoccluded AND the surface faces it
+                // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
+                const float diffuse = smax(dot3(hn, ldir), 0.0f);
+                if (!sh.occluded && diffuse > 0.0f) {
                     // PointLight::calculate_contribution_at (light.rs:261-299)
                     const float ldist = mag3(l2p) + EPS;
                     const float cosi = dot3(l2p, hn) / ldist;
-                    const bool pos = cosi > 0.0f;
-                    const float att = 0.95f * (EPS + ldist + ldist * ldist);
-                    const float sig = (tanhf(att) + 1.0f) / 2.0f;
-                    const float lfc = cosi * lint * sclamp(sig, 0.0f, 1.0f);
-                    const float3 ccolor = pos ? (m.color * lcol) : splat(0.0f);
-                    const float cint = pos ? lfc : 0.0f;
-                    const float3 lcs = ccolor / sh.filter;
-                    const float diffuse = smax(dot3(hn, ldir), 0.0f);
-                    float spec = 0.0f;
-                    const bool has_spec = m.shininess > 0.0f;
-                    if (has_spec) {
-                        float3 rr = reflected3(ldir, hn);
-                        float sd = smax(dot3(normalized3(rr), view), 0.0f);
-                        spec = powf(sd, smax(m.shininess * 512.0f, 1.0f));
-                    }
-                    const float lf = diffuse * cint * sh.opacity;
-                    const float sf = cint * sh.opacity * spec;
-                    if (diffuse > 0.0f) {
+                    if (cosi > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
+                        const float att = 0.95f * (EPS + ldist + ldist * ldist);
+                        const float sig = (tanhf(att) + 1.0f) / 2.0f;
+                        const float cint = cosi * lint * sclamp(sig, 0.0f, 1.0f);
+                        const float3 ccolor = m.color * lcol;
+                        // colour / filter; x / 1.0f == x exactly, and the filter is (1,1,1) unless the
+                        // ray crossed a transmissive primitive
+                        const bool unit_filter = sh.filter.x == 1.0f && sh.filter.y == 1.0f && sh.filter.z == 1.0f;
+                        const float3 lcs = unit_filter ? ccolor : ccolor / sh.filter;
+                        float spec = 0.0f;
+                        const bool has_spec = m.shininess > 0.0f;
+                        if (has_spec) {
+                            float3 rr = reflected3(ldir, hn);
+                            float sd = smax(dot3(normalized3(rr), view), 0.0f);
+                            spec = powf(sd, smax(m.shininess * 512.0f, 1.0f));
+                        }
+                        const float lf = diffuse * cint * sh.opacity;
+                        const float sf = cint * sh.opacity * spec;
                         dc = m.color * lcs * lf;
                         if (has_spec) spc = lcol * sf;
+                    } else {
+                        // cosi <= 0 with diffuse > 0 (rounding only): contribution colour and intensity
+                        // are zero; the specular term is l.color * (0 * opacity * spec) = 0 exactly.
+                        dc = m.color * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
                     }
                 }
             }
