@@ -99,7 +99,8 @@ def build_workload(name: str, seed: int):
 
 
 def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
-    """Brute-force oracle (the reference's linear scan) on a random pixel sample; returns rays, seconds."""
+    """Brute-force oracle (the reference's linear scan, 8-ray AVX2 packets = its `simd_render` path
+    where the config is a packet config, scalar otherwise) on a random pixel sample; returns rays, seconds."""
     from oracle import oracle
 
     W, H = rc.cfg.width, rc.cfg.height
@@ -107,7 +108,7 @@ def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
     pix = rng.choice(W * H, size=min(n_pixels, W * H), replace=False).astype(np.uint32)
     desc = flat.desc()
     t0 = time.perf_counter()
-    _, _, _, cnt = oracle.render(desc, rc.cfg, oracle.BRUTE, threads, pix)
+    _, _, _, cnt = oracle.render(desc, rc.cfg, oracle.PACKET8, threads, pix)
     dt = time.perf_counter() - t0
     return cnt["closest_rays"] + cnt["shadow_rays"], dt, len(pix)
 
@@ -119,8 +120,9 @@ def cpu_baseline(flat, rc, budget_s: float = 15.0) -> dict:
     n2 = int(max(4 * cores, min(rc.cfg.width * rc.cfg.height, budget_s / per_pixel)))
     rays, dt, n = oracle_sample(flat, rc, n2, cores)
     return {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": f"{n} random pixels of the workload ({rays} rays, {dt:.1f} s), brute-force scalar C++ oracle "
-                      f"(linear scan over all {flat.n_primitives} primitives like the reference), {cores} threads"}
+            "sample": f"{n} random pixels of the workload ({rays} rays, {dt:.1f} s), brute-force C++ oracle, "
+                      f"8-ray AVX2 packets (the reference's simd_render instantiation: linear scan over all {flat.n_primitives} "
+                      f"primitives per packet), {cores} threads"}
 
 
 def run_reference(args) -> None:
@@ -150,7 +152,7 @@ def run_reference(args) -> None:
         "config": {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
                    "step": f"{n_step} random pixels of the frame per step ({n_step / frame_pixels:.5f} of a frame)"},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_step} random pixels per step, brute-force scalar C++ oracle (the reference's linear scan), {cores} threads; "
+                         "sample": f"{n_step} random pixels per step, brute-force C++ oracle with 8-ray AVX2 packets (the reference's simd_render linear scan), {cores} threads; "
                                    "the Rust reference itself cannot be built in this image (no cargo/rustc, crates not vendored)"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ms_per_frame_extrapolated": 1e3 * (tot_t / args.steps) * frame_pixels / n_step,

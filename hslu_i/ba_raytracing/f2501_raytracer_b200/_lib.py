@@ -13,7 +13,7 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parents[2]
-LIB_PATH = PKG_DIR / "librt_b200.so"
+LIB_PATH = Path(os.environ.get("RT_LIB_PATH", PKG_DIR / "librt_b200.so"))
 
 RT_OK = 0
 RT_ERR_INVALID_ARGUMENT = -1

@@ -17,7 +17,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parents[2]
 CSRC = PKG / "csrc"
-OUT = PKG / "librt_b200.so"
+OUT = Path(os.environ.get("RT_LIB_PATH", PKG / "librt_b200.so"))  # RT_LIB_PATH / RT_NVCC_EXTRA: tuning experiments only
 
 SOURCES = [CSRC / "rt_api.cu", CSRC / "rt_bvh.cpp", CSRC / "rt_sampler.cpp", CSRC / "rt_error.cpp", CSRC / "host" / "rt_host.cpp"]
 HEADERS = [CSRC / "rt_device.cuh", CSRC / "rt_kernels.cuh", CSRC / "rt_bvh.h", CSRC / "rt_internal.h", CSRC / "host" / "rt_host.hpp",
@@ -50,6 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return OUT
     cmd = [nvcc_path(), *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{CSRC}", f"-I{CSRC / 'host'}"]
+    cmd += os.environ.get("RT_NVCC_EXTRA", "").split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", str(OUT), *map(str, SOURCES)]

@@ -37,8 +37,9 @@ struct rt_scene {
     // per-render scratch, grown on demand
     float4 *samples = nullptr;
     size_t samples_cap = 0;
-    float *clouds = nullptr;
+    float4 *clouds = nullptr;  // K x M cloud points padded to float4 (one LDG.128 per light copy)
     size_t clouds_cap = 0;
+    std::vector<float> clouds_host;
     unsigned int *work_counter = nullptr;
     unsigned long long *counters = nullptr;
     uint32_t *slab_argb = nullptr;
@@ -192,10 +193,17 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
                           uint64_t *launches) {
     fill_params(s, cfg, p);
     if (p.LM > 0 && p.M > 1) {
-        size_t bytes = (size_t)cfg->n_light_clouds * p.M * 3 * sizeof(float);
-        int rc = grow(s->clouds, s->clouds_cap, bytes);
+        const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
+        int rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4));
         if (rc) return rc;
-        CU_CHECK(cudaMemcpyAsync(s->clouds, cfg->light_clouds, bytes, cudaMemcpyHostToDevice, stream));
+        s->clouds_host.resize(4 * n_pts);
+        for (size_t i = 0; i < n_pts; i++) {
+            s->clouds_host[4 * i] = cfg->light_clouds[3 * i];
+            s->clouds_host[4 * i + 1] = cfg->light_clouds[3 * i + 1];
+            s->clouds_host[4 * i + 2] = cfg->light_clouds[3 * i + 2];
+            s->clouds_host[4 * i + 3] = 0.0f;
+        }
+        CU_CHECK(cudaMemcpyAsync(s->clouds, s->clouds_host.data(), n_pts * sizeof(float4), cudaMemcpyHostToDevice, stream));
         p.clouds = s->clouds;
     }
     size_t n_samples = (size_t)p.local_rows * p.width * p.S;

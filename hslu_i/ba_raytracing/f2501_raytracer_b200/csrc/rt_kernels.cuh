@@ -15,7 +15,15 @@
 
 namespace rtd {
 
-constexpr int CTA_THREADS = 256;
+// Occupancy sweep on B200 (profiles/README.md): the kernel is latency bound, 28 warps/SM at 72
+// registers (a few hundred bytes of spills) beats 16 warps/SM at 125 registers without spills by 13 %.
+#ifndef RT_CTA_THREADS
+#define RT_CTA_THREADS 128
+#endif
+#ifndef RT_MIN_CTAS_PER_SM
+#define RT_MIN_CTAS_PER_SM 7
+#endif
+constexpr int CTA_THREADS = RT_CTA_THREADS;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
 constexpr int PATH_STACK = 24;   // >= 1 + max(reflection, refraction) depth (21) + slack
 constexpr int MAX_AA = 24;
@@ -33,7 +41,7 @@ struct RenderParams {
     float eps_d;           // default_epsilon_distance component (vector.rs:697-700)
     float aa_off[2 * MAX_AA];
     float sample_scale;    // 1 / S
-    const float *clouds;   // K x M x 3
+    const float4 *clouds;  // K x M points, padded to float4
     uint32_t K;
     unsigned long long seed;
     uint32_t refl_depth, refr_depth;
@@ -67,13 +75,13 @@ struct PathRec {  // one pending ray of a sample's reflection/refraction tree (4
 constexpr uint32_t PATH_REFL_CHILD = 1u << 16;  // whole subtree is scaled by attenuation(t) of its first hit
 
 struct WarpShared {
-    float4 rec[32][3];               // hit records: (P, n.x) (n.yz, v.xy) (v.z, bits mat, bits pixel x, bits pixel y)
+    float4 rec[32][4];               // hit records: (P, n.x) (n.yz, v.xy) (v.z, bits mat, bits pixel x, bits pixel y) (material colour, shininess)
     float res[32][6];                // per pair: diffuse rgb, specular rgb (only when fewer than 32 hits are live)
     uint32_t cloud[32][MAX_SM_LIGHTS];
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel(const RenderParams p) {
     __shared__ WarpShared smem[CTA_WARPS];
     WarpShared &ws = smem[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31;
@@ -185,6 +193,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
             ws.rec[my_slot][0] = make_float4(P.x, P.y, P.z, N.x);
             ws.rec[my_slot][1] = make_float4(N.y, N.z, d.x, d.y);
             ws.rec[my_slot][2] = make_float4(d.z, __uint_as_float(h.meta & rtb::PRIM_MATERIAL_MASK), __uint_as_float(pix_x), __uint_as_float(pix_y));
+            const float4 ma = __ldg(sc.mats + 3 * (h.meta & rtb::PRIM_MATERIAL_MASK)), mb = __ldg(sc.mats + 3 * (h.meta & rtb::PRIM_MATERIAL_MASK) + 1);
+            ws.rec[my_slot][3] = make_float4(ma.x, ma.y, ma.z, mb.x);
         }
         // lane s < n_live accumulates the light sums of hit slot s (in light order, like the
         // reference's `for light in lights`); when all 32 lanes are live, slot == lane == owner.
@@ -207,10 +217,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
             if (pair < total) {
                 // light-major flattening: a batch holds ONE light copy for (up to) 32 neighbouring hit
                 // points, so the 32 shadow rays converge on the same point and traverse together
-                const uint32_t l = pair / n_live, s = pair - l * n_live;
-                const float4 r0 = ws.rec[s][0], r1 = ws.rec[s][1], r2 = ws.rec[s][2];
+                // (n_live == 32: l = base / 32 and s = lane, no division)
+                const uint32_t l = n_live == 32 ? (base >> 5) : pair / n_live, s = pair - l * n_live;
+                const float4 r0 = ws.rec[s][0], r1 = ws.rec[s][1], r2 = ws.rec[s][2], r3 = ws.rec[s][3];
                 const float3 hp = f3(r0.x, r0.y, r0.z), hn = f3(r0.w, r1.x, r1.y), view = f3(r1.z, r1.w, r2.x);
-                const Material m = load_material(sc, __float_as_uint(r2.y));
+                const float3 mcolor = f3(r3.x, r3.y, r3.z);
+                const float mshininess = r3.w;
                 uint32_t li = l, cpy = 0;
                 if (p.M > 1) {
                     li = l / p.M;
@@ -224,8 +236,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
                     uint32_t ci = li < MAX_SM_LIGHTS
                                       ? ws.cloud[s][li]
                                       : cloud_index(p.seed, packet_noaa ? __float_as_uint(r2.z) / 8u : __float_as_uint(r2.z), __float_as_uint(r2.w), li, p.K);
-                    const float *cp = p.clouds + ((size_t)ci * p.M + cpy) * 3;
-                    float3 rp = f3(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2));
+                    const float4 cp = __ldg(p.clouds + (size_t)ci * p.M + cpy);
+                    float3 rp = f3(cp.x, cp.y, cp.z);
                     lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
                     lint = p.inv_M * lint;
                 }
@@ -246,26 +258,26 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) render_kernel(const RenderPara
                         const float att = 0.95f * (EPS + ldist + ldist * ldist);
                         const float sig = (tanhf(att) + 1.0f) / 2.0f;
                         const float cint = cosi * lint * sclamp(sig, 0.0f, 1.0f);
-                        const float3 ccolor = m.color * lcol;
+                        const float3 ccolor = mcolor * lcol;
                         // colour / filter; x / 1.0f == x exactly, and the filter is (1,1,1) unless the
                         // ray crossed a transmissive primitive
                         const bool unit_filter = sh.filter.x == 1.0f && sh.filter.y == 1.0f && sh.filter.z == 1.0f;
                         const float3 lcs = unit_filter ? ccolor : ccolor / sh.filter;
                         float spec = 0.0f;
-                        const bool has_spec = m.shininess > 0.0f;
+                        const bool has_spec = mshininess > 0.0f;
                         if (has_spec) {
                             float3 rr = reflected3(ldir, hn);
                             float sd = smax(dot3(normalized3(rr), view), 0.0f);
-                            spec = powf(sd, smax(m.shininess * 512.0f, 1.0f));
+                            spec = powf(sd, smax(mshininess * 512.0f, 1.0f));
                         }
                         const float lf = diffuse * cint * sh.opacity;
                         const float sf = cint * sh.opacity * spec;
-                        dc = m.color * lcs * lf;
+                        dc = mcolor * lcs * lf;
                         if (has_spec) spc = lcol * sf;
                     } else {
                         // cosi <= 0 with diffuse > 0 (rounding only): contribution colour and intensity
                         // are zero; the specular term is l.color * (0 * opacity * spec) = 0 exactly.
-                        dc = m.color * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
+                        dc = mcolor * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
                     }
                 }
             }

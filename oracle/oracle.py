@@ -41,7 +41,7 @@ def load() -> C.CDLL:
     return _lib
 
 
-BRUTE, BVH = 0, 1
+BRUTE, BVH, PACKET8 = 0, 1, 2
 
 
 def render(desc, cfg, mode: int = BVH, threads: int = 0, pixels: np.ndarray | None = None, want_rgb: bool = False):

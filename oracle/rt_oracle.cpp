@@ -20,7 +20,12 @@
 //
 // A second mode (mode = 1) swaps the two linear scans for a private median-split BVH; it is
 // proven bit-identical to mode 0 by tests/test_oracle_bvh.py and exists only so that
-// full-frame oracle images are affordable.
+// full-frame oracle images are affordable.  A third mode (mode = 2) is the CPU-baseline stand-in
+// for the reference's `simd_render` feature: the same linear scans, 8 rays per AVX2 packet
+// against one object at a time (Vec3x8 instantiation, raytracer.rs:48-50,180-182), bit-identical
+// to mode 0 per lane (tests/test_oracle_bvh.py); used only for timing by bench.py.
+#include <immintrin.h>
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -525,6 +530,153 @@ struct Tracer {
         }
         return s;
     }
+
+    // ------------------------------------------------------------------------------------------
+    // mode 2: 8-ray packets (the `simd_render` instantiation of the same two loops)
+    struct V8 {
+        __m256 x, y, z;
+    };
+    static inline __m256 dot8(const V8 &a, const V8 &b) { return _mm256_fmadd_ps(a.x, b.x, _mm256_fmadd_ps(a.y, b.y, _mm256_mul_ps(a.z, b.z))); }
+    static inline V8 splat8(V3 v) { return {_mm256_set1_ps(v.x), _mm256_set1_ps(v.y), _mm256_set1_ps(v.z)}; }
+    static inline V8 cross8(const V8 &a, const V8 &b) {
+        const __m256 sign = _mm256_set1_ps(-0.0f);
+        return {_mm256_fmadd_ps(a.y, b.z, _mm256_xor_ps(sign, _mm256_mul_ps(a.z, b.y))),
+                _mm256_fmadd_ps(a.z, b.x, _mm256_xor_ps(sign, _mm256_mul_ps(a.x, b.z))),
+                _mm256_fmadd_ps(a.x, b.y, _mm256_xor_ps(sign, _mm256_mul_ps(a.y, b.x)))};
+    }
+    static inline V8 scale8(const V8 &a, __m256 s) { return {_mm256_mul_ps(a.x, s), _mm256_mul_ps(a.y, s), _mm256_mul_ps(a.z, s)}; }
+    // a.x*b.x + a.y*b.y + a.z*b.z, unfused, left to right (Mat3 * Vec3)
+    static inline __m256 mv8(const V8 &a, const V8 &b) {
+        return _mm256_add_ps(_mm256_add_ps(_mm256_mul_ps(a.x, b.x), _mm256_mul_ps(a.y, b.y)), _mm256_mul_ps(a.z, b.z));
+    }
+
+    // TriangleData::intersect for 8 rays: lane mask of valid hits and their t
+    inline int tri_intersect8(const Prim &tr, const Mat &m, const V8 &o, const V8 &d, __m256 &t_out) {
+        cn.tri += 8;
+        const __m256 sign = _mm256_set1_ps(-0.0f), eps = _mm256_set1_ps(EPS), zero = _mm256_setzero_ps(), one = _mm256_set1_ps(1.0f);
+        __m256 visible = _mm256_castsi256_ps(_mm256_set1_epi32(-1));
+        if (cull) {
+            visible = _mm256_cmp_ps(dot8(d, splat8(tr.n)), _mm256_set1_ps(0.75f), _CMP_LT_OQ);
+            if (m.transmissive()) visible = _mm256_castsi256_ps(_mm256_set1_epi32(-1));
+            if (_mm256_movemask_ps(visible) == 0) return 0;
+        }
+        const V8 a = splat8(tr.a);
+        const V8 b = {_mm256_sub_ps(a.x, o.x), _mm256_sub_ps(a.y, o.y), _mm256_sub_ps(a.z, o.z)};
+        const V8 c1 = splat8(-tr.e1), c2 = splat8(-tr.e2);
+        const V8 x = cross8(c1, c2), y = cross8(c2, d), z = cross8(d, c1);
+        const __m256 det = dot8(d, x);
+        const __m256 inv = _mm256_div_ps(one, det);
+        const V8 X = scale8(x, inv), Y = scale8(y, inv), Z = scale8(z, inv);
+        const __m256 t = mv8(X, b), u = mv8(Y, b), v = mv8(Z, b);
+        // determinant: cofactor expansion along the first row, unfused
+        const __m256 m0 = _mm256_sub_ps(_mm256_mul_ps(c1.y, c2.z), _mm256_mul_ps(c2.y, c1.z));
+        const __m256 m1 = _mm256_sub_ps(_mm256_mul_ps(d.y, c2.z), _mm256_mul_ps(c2.y, d.z));
+        const __m256 m2 = _mm256_sub_ps(_mm256_mul_ps(d.y, c1.z), _mm256_mul_ps(c1.y, d.z));
+        const __m256 det2 = _mm256_add_ps(_mm256_sub_ps(_mm256_mul_ps(d.x, m0), _mm256_mul_ps(c1.x, m1)), _mm256_mul_ps(c2.x, m2));
+        const __m256 t_inv = _mm256_cmp_ps(t, eps, _CMP_LE_OQ);
+        const __m256 uv_inv = _mm256_or_ps(_mm256_or_ps(_mm256_cmp_ps(u, zero, _CMP_LT_OQ), _mm256_cmp_ps(v, zero, _CMP_LT_OQ)),
+                                           _mm256_cmp_ps(_mm256_add_ps(u, v), one, _CMP_GE_OQ));
+        const __m256 det_zero = _mm256_cmp_ps(_mm256_andnot_ps(sign, _mm256_sub_ps(det2, zero)), eps, _CMP_LE_OQ);
+        const __m256 valid = _mm256_andnot_ps(det_zero, _mm256_andnot_ps(_mm256_or_ps(t_inv, uv_inv), visible));
+        t_out = t;
+        return _mm256_movemask_ps(valid);
+    }
+
+    // Raytracer::cast_ray, Vec3x8 instantiation: every object against the 8-ray packet
+    void cast_ray8(const Ray rays[8], Hit out[8]) {
+        cn.closest += 8;
+        float buf[6][8];
+        for (int l = 0; l < 8; l++) {
+            buf[0][l] = rays[l].o.x; buf[1][l] = rays[l].o.y; buf[2][l] = rays[l].o.z;
+            buf[3][l] = rays[l].d.x; buf[4][l] = rays[l].d.y; buf[5][l] = rays[l].d.z;
+        }
+        const V8 o = {_mm256_loadu_ps(buf[0]), _mm256_loadu_ps(buf[1]), _mm256_loadu_ps(buf[2])};
+        const V8 d = {_mm256_loadu_ps(buf[3]), _mm256_loadu_ps(buf[4]), _mm256_loadu_ps(buf[5])};
+        bool cur_valid[8] = {false};
+        float cur_t[8] = {0};
+        uint32_t cur_prim[8] = {0};
+        Hit h;
+        for (uint32_t i = 0; i < sc.prims.size(); i++) {
+            const Prim &p = sc.prims[i];
+            if (p.kind == 0) {  // few spheres: lane by lane
+                for (int l = 0; l < 8; l++) {
+                    h.valid = false;
+                    cn.sph++;
+                    if (sph_intersect(p, sc.mats[p.mat], rays[l], cull, h) && h.valid && (!cur_valid[l] || h.t <= cur_t[l])) {
+                        cur_valid[l] = true;
+                        cur_t[l] = h.t;
+                        cur_prim[l] = i;
+                    }
+                }
+                continue;
+            }
+            __m256 t8;
+            int mask = tri_intersect8(p, sc.mats[p.mat], o, d, t8);
+            if (!mask) continue;
+            float tt[8];
+            _mm256_storeu_ps(tt, t8);
+            for (int l = 0; l < 8; l++) {
+                if (!(mask >> l & 1)) continue;
+                if (!cur_valid[l] || tt[l] <= cur_t[l]) {  // ties: the later object wins; a NaN t never replaces
+                    cur_valid[l] = true;
+                    cur_t[l] = tt[l];
+                    cur_prim[l] = i;
+                }
+            }
+        }
+        Counters scratch;
+        for (int l = 0; l < 8; l++) {
+            out[l] = Hit();
+            if (!cur_valid[l]) continue;
+            // rebuild the full interaction with the scalar code (same arithmetic, same result)
+            std::swap(cn, scratch);
+            prim_intersect(sc, cur_prim[l], rays[l], cull, out[l], cn);
+            std::swap(cn, scratch);
+        }
+    }
+
+    // Raytracer::has_any_intersection, Vec3x8 instantiation
+    void has_any_intersection8(const V3 from[8], const V3 dir[8], const float maxd[8], Shadow out[8]) {
+        cn.shadow += 8;
+        Ray rays[8];
+        float buf[7][8];
+        for (int l = 0; l < 8; l++) {
+            rays[l] = make_ray(from[l], dir[l]);
+            buf[0][l] = rays[l].o.x; buf[1][l] = rays[l].o.y; buf[2][l] = rays[l].o.z;
+            buf[3][l] = rays[l].d.x; buf[4][l] = rays[l].d.y; buf[5][l] = rays[l].d.z;
+            buf[6][l] = maxd[l];
+            out[l] = Shadow();
+        }
+        const V8 o = {_mm256_loadu_ps(buf[0]), _mm256_loadu_ps(buf[1]), _mm256_loadu_ps(buf[2])};
+        const V8 d = {_mm256_loadu_ps(buf[3]), _mm256_loadu_ps(buf[4]), _mm256_loadu_ps(buf[5])};
+        const __m256 md = _mm256_loadu_ps(buf[6]);
+        Counters scratch;
+        Hit h;
+        for (uint32_t i = 0; i < sc.prims.size(); i++) {
+            const Prim &p = sc.prims[i];
+            int mask = 0;
+            if (p.kind == 0) {
+                mask = 0xFF;  // resolved lane by lane below
+            } else {
+                __m256 t8;
+                mask = tri_intersect8(p, sc.mats[p.mat], o, d, t8);
+                mask &= _mm256_movemask_ps(_mm256_cmp_ps(t8, md, _CMP_LE_OQ));
+            }
+            if (!mask) continue;
+            for (int l = 0; l < 8; l++) {
+                if (!(mask >> l & 1) || out[l].occluded) continue;
+                std::swap(cn, scratch);
+                bool some = prim_intersect(sc, i, rays[l], cull, h, cn);
+                std::swap(cn, scratch);
+                if (p.kind == 0) cn.sph++;
+                if (some) shadow_accumulate(sc, rays[l], h, maxd[l], out[l]);
+            }
+            // `if completely_occluded.all() && has_intersection.all() { break }` (raytracer.rs:94-96)
+            bool all = true;
+            for (int l = 0; l < 8; l++) all = all && out[l].occluded;
+            if (all) break;
+        }
+    }
 };
 
 // ------------------------------------------------------------------------------------------
@@ -702,6 +854,76 @@ struct Renderer {
         return c.color * boost * transmittance;
     }
 
+    // single_raytrace + calculate_lighting for one 8-ray packet without bounces (mode 2 timing
+    // path). Per lane identical to the scalar functions above; lanes that missed keep tracing
+    // shadow packets with non-finite rays like the reference's masked lanes do.
+    void single_raytrace8(const Ray rays[8], const std::vector<PLight> &lights, Result out[8]) {
+        Hit hit[8];
+        tr.cast_ray8(rays, hit);
+        bool any = false;
+        for (int l = 0; l < 8; l++) any = any || hit[l].valid;
+        for (int l = 0; l < 8; l++) out[l] = Result();
+        if (!any) return;  // `if nearest_interaction.valid_mask.none() { return None }`
+        V3 light_color[8], specular_color[8];
+        for (int l = 0; l < 8; l++) light_color[l] = specular_color[l] = splat(0.0f);
+        const float nanv = std::numeric_limits<float>::quiet_NaN();
+        for (const PLight &lt : lights) {
+            V3 from[8], dirs[8], l2p[8], ldir[8];
+            float maxd[8];
+            for (int l = 0; l < 8; l++) {
+                if (!hit[l].valid) {
+                    from[l] = dirs[l] = l2p[l] = ldir[l] = splat(nanv);
+                    maxd[l] = nanv;
+                    continue;
+                }
+                l2p[l] = lt.pos - hit[l].p;
+                ldir[l] = normalized(l2p[l]);
+                from[l] = hit[l].p + ldir[l] * k.eps_d;
+                dirs[l] = ldir[l];
+                maxd[l] = mag(lt.pos - from[l]);
+            }
+            Shadow sh[8];
+            tr.has_any_intersection8(from, dirs, maxd, sh);
+            for (int l = 0; l < 8; l++) {
+                if (!hit[l].valid || sh[l].occluded) continue;
+                const Mat &m = sc.mats[hit[l].mat];
+                float light_distance = mag(l2p[l]) + EPS;
+                float cosi = dot(l2p[l], hit[l].n) / light_distance;
+                bool pos = cosi > 0.0f;
+                float att = 0.95f * (EPS + light_distance + light_distance * light_distance);
+                float sig = (tanhf(att) + 1.0f) / 2.0f;
+                float lfc = cosi * lt.intensity * sclamp(sig, 0.0f, 1.0f);
+                V3 ccolor = pos ? (m.color * lt.color) : splat(0.0f);
+                float cint = pos ? lfc : 0.0f;
+                V3 lcs = ccolor / sh[l].filter;
+                float diffuse = smax(dot(hit[l].n, ldir[l]), 0.0f);
+                bool has_specular = m.shininess > 0.0f;
+                float spec = 0.0f;
+                if (has_specular) {
+                    V3 r = reflected(ldir[l], hit[l].n);
+                    spec = powf(smax(dot(normalized(r), rays[l].d), 0.0f), smax(m.shininess * 512.0f, 1.0f));
+                }
+                float lf = diffuse * cint * sh[l].opacity;
+                float sf = cint * sh[l].opacity * spec;
+                if (diffuse > 0.0f) {
+                    light_color[l] = light_color[l] + m.color * lcs * lf;
+                    if (has_specular) specular_color[l] = specular_color[l] + lt.color * sf;
+                }
+            }
+        }
+        for (int l = 0; l < 8; l++) {
+            if (!hit[l].valid) continue;
+            const Mat &m = sc.mats[hit[l].mat];
+            V3 ambient = (m.color * splat(1.0f)) * 0.08f;
+            float df = attenuation(hit[l].t);
+            V3 direct = (ambient + light_color[l]) * df;
+            V3 specular = specular_color[l] * df;
+            out[l].valid = true;
+            out[l].t = hit[l].t;
+            out[l].color = m.transmissive() ? (splat(0.0f) + splat(0.0f) + specular) : (direct + splat(0.0f) + specular);
+        }
+    }
+
     // SceneLightSource::preprocess -> PointLight::to_point_light_cloud (light.rs:183-225,311-324)
     void pixel_lights(uint32_t px, uint32_t py, std::vector<PLight> &out) {
         uint32_t M = cfg.light_multiplicator ? cfg.light_multiplicator : 1;
@@ -769,7 +991,18 @@ struct Renderer {
         float scale = 1.0f / (float)S;
         bool any = false;
         std::vector<V3> c(S);
-        for (uint32_t i = 0; i < S; i++) {
+        const bool packets = tr.mode == 2 && (cfg.flags & F_PACKET) && !refl_on && !refr_on && S % 8 == 0;
+        for (uint32_t i = 0; i < S && packets; i += 8) {  // one Vec3x8 packet = 8 samples of this pixel
+            Ray rays[8];
+            for (int l = 0; l < 8; l++) rays[l] = make_ray({coords.x + off[2 * (i + l)], coords.y + off[2 * (i + l) + 1], coords.z}, dir);
+            Result r8[8];
+            single_raytrace8(rays, lights, r8);
+            for (int l = 0; l < 8; l++) {
+                any = any || r8[l].valid;
+                c[i + l] = r8[l].valid ? r8[l].color * scale : splat(0.0f);
+            }
+        }
+        for (uint32_t i = 0; i < S && !packets; i++) {
             V3 o = {coords.x + off[2 * i], coords.y + off[2 * i + 1], coords.z};
             Result r = single_raytrace(o, dir, AIR_IOR, lights, -1);
             any = any || r.valid;

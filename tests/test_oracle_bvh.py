@@ -42,3 +42,19 @@ def test_rendered_pixels_identical_with_bounces_and_soft_shadows(pkg, oracle_mod
     assert np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
     assert n0["closest_rays"] == n1["closest_rays"] and n0["shadow_rays"] == n1["shadow_rays"]
     assert n1["triangle_tests"] < n0["triangle_tests"] / 20
+
+
+def test_packet8_mode_identical_to_scalar_scan(pkg, oracle_mod):
+    """mode 2 (8-ray AVX2 packets, the `simd_render` stand-in timed by bench.py) == mode 0 per lane."""
+    feat = "high_quality,simd_render"
+    flat = pkg.example_scene("main", "").flatten()  # lowres text keeps the brute-force scan short
+    rc = pkg.RenderConfig.from_features(feat, 5, n_light_clouds=64)
+    rng = np.random.default_rng(8)
+    pix = rng.choice(rc.cfg.width * rc.cfg.height, 16, replace=False).astype(np.uint32)
+    pix = np.concatenate([pix, np.array([100 * 768 + 30, 320 * 768 + 384], np.uint32)])
+    a0, m0, c0, n0 = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BRUTE, 0, pix, want_rgb=True)
+    a2, m2, c2, n2 = oracle_mod.render(flat.desc(), rc.cfg, 2, 0, pix, want_rgb=True)
+    assert np.array_equal(m0, m2) and np.array_equal(a0, a2)
+    assert np.array_equal(c0.view(np.uint32), c2.view(np.uint32))
+    assert n0["closest_rays"] == n2["closest_rays"]
+    assert n2["shadow_rays"] >= n0["shadow_rays"]  # masked (missed) lanes still ride along in a packet
