@@ -39,6 +39,8 @@ WORKLOADS = {
     "c1lite": ("main", "", "main.rs --no-default-features 768x640"),
     "c2": ("test_scene", "simd_render,backface_culling,medium_resolution", "examples/test_scene 1140x950 (BASELINE configs[1])"),
     "c4": ("semesterbild", "realistic,high_resolution", "semesterbild realistic high_resolution 1620x1350 depth 9/8 (BASELINE configs[3])"),
+    "c5": ("large_mesh", "extreme_quality,realistic,high_resolution,simd_render",
+           "semesterbild objects + synthetic 4 194 304-triangle relief, extreme_quality+realistic 1620x1350 S=24 M=28 depth 21/21 (BASELINE configs[4])"),
 }
 # canonical algorithmic costs
 F_BOX, F_TRI, F_SPH = 22, 45, 22
@@ -93,7 +95,12 @@ def build_workload(name: str, seed: int):
     from hslu_i.ba_raytracing.f2501_raytracer_b200 import RenderConfig, example_scene
 
     scene_name, features, desc = WORKLOADS[name]
-    flat = example_scene(scene_name, features).flatten()
+    if scene_name == "large_mesh":
+        from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+        flat = large_mesh_scene(features).flatten()
+    else:
+        flat = example_scene(scene_name, features).flatten()
     rc = RenderConfig.from_features(features, seed)
     return flat, rc, features, desc
 

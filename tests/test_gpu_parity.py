@@ -191,6 +191,32 @@ def test_test_scene_with_everything_on(pkg, oracle_mod, scenes):
                seed=9, width=380, height=316, n_light_clouds=256)
 
 
+def test_large_synthetic_mesh(pkg, oracle_mod):
+    """BASELINE configs[4] at reduced size: semesterbild objects + a 524 288-triangle relief, bounces,
+    AA and soft shadows; every 7th pixel of a 405x337 frame, plus raw queries against the big BVH."""
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+    feat = "high_quality,realistic,simd_render"
+    flat = large_mesh_scene(feat, nx=512, ny=512).flatten()
+    assert len(flat.triangles) == 2 * 512 * 512 + 48
+    dev = pkg.DeviceScene(flat)
+    try:
+        rng = np.random.default_rng(4)
+        rays = random_rays(rng, 50000)
+        t_g, p_g = dev.trace_closest(rays)
+        t_o, p_o = oracle_mod.trace_closest(flat.desc(), rays, 0, oracle_mod.BVH)
+        assert np.array_equal(p_g, p_o) and np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))
+        assert (p_o >= 9 + 48).mean() > 0.1  # the relief itself is hit
+        rc = pkg.RenderConfig.from_features(feat, 6, width=405, height=337, n_light_clouds=512)
+        buf, _ = dev.render(rc)
+        ys, xs = np.mgrid[0:337:7, 0:405:7]
+        pix = (ys * 405 + xs).astype(np.uint32).ravel()
+        o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+        assert_image_parity(buf, o_argb, o_mask, pix)
+    finally:
+        dev.close()
+
+
 # ---------------------------------------------------------------- properties at full size
 def test_render_is_deterministic_and_seed_sensitive(pkg, scenes):
     feat = "high_quality,simd_render"
