@@ -37,7 +37,7 @@ pub struct RtConfig {
     width: u32, height: u32, flags: u32, aa_samples_per_pixel: u32,
     aa_table: *const f32, aa_table_len: u32, light_multiplicator: u32,
     light_clouds: *const f32, n_light_clouds: u32, reflection_max_depth: u32, refraction_max_depth: u32,
-    seed: u64, tile_rows: u32, tile_rank: u32, tile_world: u32, reserved: u32,
+    seed: u64, tile_rows: u32, tile_rank: u32, tile_world: u32, tables_epoch: u32,
 }
 #[repr(C)]
 pub struct RtScene { _private: [u8; 0] }
@@ -144,7 +144,7 @@ where
             light_clouds: if m > 1 { clouds.as_ptr() } else { std::ptr::null() }, n_light_clouds: if m > 1 { n_clouds } else { 0 },
             reflection_max_depth: if hq { if xq { 21 } else { 13 } } else { 9 },
             refraction_max_depth: if hq { if xq { 21 } else { 18 } } else { 8 },
-            seed, tile_rows: 0, tile_rank: 0, tile_world: 1, reserved: 0,
+            seed, tile_rows: 0, tile_rank: 0, tile_world: 1, tables_epoch: 0,
         };
 
         // ---- render straight into the ImageBuffer: [AtomicU32; W*H] is layout-identical to [u32; W*H]

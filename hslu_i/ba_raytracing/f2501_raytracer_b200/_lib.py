@@ -58,7 +58,7 @@ class Config(C.Structure):
         ("aa_table", C.c_void_p), ("aa_table_len", C.c_uint32), ("light_multiplicator", C.c_uint32),
         ("light_clouds", C.c_void_p), ("n_light_clouds", C.c_uint32), ("reflection_max_depth", C.c_uint32),
         ("refraction_max_depth", C.c_uint32), ("seed", C.c_uint64),
-        ("tile_rows", C.c_uint32), ("tile_rank", C.c_uint32), ("tile_world", C.c_uint32), ("reserved", C.c_uint32),
+        ("tile_rows", C.c_uint32), ("tile_rank", C.c_uint32), ("tile_world", C.c_uint32), ("tables_epoch", C.c_uint32),
     ]
 
 

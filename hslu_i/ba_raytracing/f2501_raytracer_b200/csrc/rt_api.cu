@@ -40,6 +40,8 @@ struct rt_scene {
     float4 *clouds = nullptr;  // K x M cloud points padded to float4 (one LDG.128 per light copy)
     size_t clouds_cap = 0;
     std::vector<float> clouds_host;
+    uint32_t clouds_epoch = 0, clouds_k = 0, clouds_m = 0;  // what the device copy currently holds
+    const float *clouds_src = nullptr;
     unsigned int *work_counter = nullptr;
     unsigned long long *counters = nullptr;
     uint32_t *slab_argb = nullptr;
@@ -194,16 +196,24 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     fill_params(s, cfg, p);
     if (p.LM > 0 && p.M > 1) {
         const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
-        int rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4));
-        if (rc) return rc;
-        s->clouds_host.resize(4 * n_pts);
-        for (size_t i = 0; i < n_pts; i++) {
-            s->clouds_host[4 * i] = cfg->light_clouds[3 * i];
-            s->clouds_host[4 * i + 1] = cfg->light_clouds[3 * i + 1];
-            s->clouds_host[4 * i + 2] = cfg->light_clouds[3 * i + 2];
-            s->clouds_host[4 * i + 3] = 0.0f;
+        const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
+                            cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && s->clouds;
+        if (!cached) {
+            int rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4));
+            if (rc) return rc;
+            s->clouds_host.resize(4 * n_pts);
+            for (size_t i = 0; i < n_pts; i++) {
+                s->clouds_host[4 * i] = cfg->light_clouds[3 * i];
+                s->clouds_host[4 * i + 1] = cfg->light_clouds[3 * i + 1];
+                s->clouds_host[4 * i + 2] = cfg->light_clouds[3 * i + 2];
+                s->clouds_host[4 * i + 3] = 0.0f;
+            }
+            CU_CHECK(cudaMemcpyAsync(s->clouds, s->clouds_host.data(), n_pts * sizeof(float4), cudaMemcpyHostToDevice, stream));
+            s->clouds_epoch = cfg->tables_epoch;
+            s->clouds_src = cfg->light_clouds;
+            s->clouds_k = cfg->n_light_clouds;
+            s->clouds_m = p.M;
         }
-        CU_CHECK(cudaMemcpyAsync(s->clouds, s->clouds_host.data(), n_pts * sizeof(float4), cudaMemcpyHostToDevice, stream));
         p.clouds = s->clouds;
     }
     size_t n_samples = (size_t)p.local_rows * p.width * p.S;
@@ -219,6 +229,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     int grid = s->sm_count * (count ? s->ctas_per_sm_count : s->ctas_per_sm);
     uint32_t warps_needed = (p.n_items + 31) / 32;
     grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, (warps_needed + CTA_WARPS - 1) / CTA_WARPS));
+    p.tail_div = 2u * (uint32_t)grid * CTA_WARPS;
     if (count)
         render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
     else

@@ -47,6 +47,7 @@ struct RenderParams {
     uint32_t refl_depth, refr_depth;
     uint32_t tile_rows, tile_rank, tile_world, local_rows;
     uint32_t tiles_x, n_items;
+    uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
     unsigned int *work_counter;
     unsigned long long *counters;  // closest, shadow, box, tri, sph
@@ -127,12 +128,23 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
             bool need = !have_ray;
             uint32_t need_mask = __ballot_sync(FULL, need);
             if (need_mask) {
-                uint32_t base = 0;
-                int leader = __ffs(need_mask) - 1;
-                if ((int)lane == leader) base = atomicAdd(p.work_counter, (unsigned int)__popc(need_mask));
+                // Guided self-scheduling: a warp normally takes one item per idle lane (up to 32), but
+                // near the end of the frame only its fair share of what is left, so that the last
+                // rounds are short and all warps finish together. Small rounds cost nothing extra:
+                // the (hit, light) flattening below fills the lanes whatever the number of live hits.
+                uint32_t base = 0, grant = 0;
+                const int leader = __ffs(need_mask) - 1;
+                if ((int)lane == leader) {
+                    const uint32_t done = *(volatile unsigned int *)p.work_counter;
+                    const uint32_t left = done < p.n_items ? p.n_items - done : 0u;
+                    grant = min((uint32_t)__popc(need_mask), max(min(left / p.tail_div + 1u, 32u), 4u));
+                    base = atomicAdd(p.work_counter, grant);
+                }
                 base = __shfl_sync(FULL, base, leader);
-                uint32_t item = base + __popc(need_mask & ((1u << lane) - 1u));
-                if (need && item < p.n_items) {
+                grant = __shfl_sync(FULL, grant, leader);
+                const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
+                const uint32_t item = base + rank;
+                if (need && rank < grant && item < p.n_items) {
                     uint32_t pix = item / p.S, s = item - pix * p.S;
                     uint32_t tile = pix / (TILE_W * TILE_H), within = pix - tile * (TILE_W * TILE_H);
                     uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;

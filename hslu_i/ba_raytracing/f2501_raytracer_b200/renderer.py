@@ -8,12 +8,15 @@ of librt_b200.so; there is no Python, PyTorch or CPU implementation of the path.
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+import itertools
+from dataclasses import dataclass
 
 import numpy as np
 
 from . import _lib as L
 from .scene import FlatScene, Scene
+
+_EPOCHS = itertools.count(1)  # rt_config.tables_epoch values: one per freshly generated set of sampler tables
 
 
 @dataclass
@@ -43,6 +46,7 @@ class RenderConfig:
             cfg.height = height
         cfg.flags |= extra_flags
         cfg.seed = seed
+        cfg.tables_epoch = next(_EPOCHS)  # the tables below are never modified in place
         aa = np.zeros((cfg.aa_table_len, 2), np.float32)
         L.check(lib.rt_sampler_aa_table(seed, cfg.aa_samples_per_pixel, rnd.value, L.ptr(aa), cfg.aa_table_len))
         cfg.aa_table = aa.ctypes.data
@@ -58,6 +62,13 @@ class RenderConfig:
         c = L.Config()
         C.memmove(C.byref(c), C.byref(self.cfg), C.sizeof(L.Config))
         c.tile_rows, c.tile_rank, c.tile_world = tile_rows, rank, world
+        return RenderConfig(c, self.aa_table, self.light_clouds, self.features, self.high_quality_model, self.scene_backface_culling)
+
+    def uncached(self) -> "RenderConfig":
+        """Same config with tables_epoch = 0: the sampler tables are re-uploaded on every call."""
+        c = L.Config()
+        C.memmove(C.byref(c), C.byref(self.cfg), C.sizeof(L.Config))
+        c.tables_epoch = 0
         return RenderConfig(c, self.aa_table, self.light_clouds, self.features, self.high_quality_model, self.scene_backface_culling)
 
     @property

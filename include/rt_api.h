@@ -124,7 +124,10 @@ typedef struct rt_config {
     uint32_t tile_rows;
     uint32_t tile_rank;
     uint32_t tile_world;
-    uint32_t reserved;
+    /* Caller-managed change counter of the CONTENTS of aa_table / light_clouds. 0 = the tables are
+       uploaded on every call. Non-zero = if the previous render call on this rt_scene had the same
+       epoch, pointers and sizes, the device copy of light_clouds is reused (no host-to-device copy). */
+    uint32_t tables_epoch;
 } rt_config;
 
 /* Work counters (RT_FLAG_COUNT_WORK) and timings. A "ray" is one closest-hit query

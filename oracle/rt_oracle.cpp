@@ -76,7 +76,7 @@ struct OConfig {
     const float *light_clouds;
     uint32_t n_light_clouds, reflection_max_depth, refraction_max_depth;
     uint64_t seed;
-    uint32_t tile_rows, tile_rank, tile_world, reserved;
+    uint32_t tile_rows, tile_rank, tile_world, tables_epoch;
 };
 enum {
     F_AA = 1u << 0,
