@@ -326,7 +326,7 @@ def main() -> None:
             "ms_per_frame": ms_per_step,
             "e2e": {"value": rays_per_frame / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_frame": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(args.steps * (2 + (0 if world == 1 else 2 * world))),
+            "gpu_launches": int(args.steps * (int(st["kernel_launches"]) + (0 if world == 1 else 2 * world))),
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
                          "frac": ach_tflops / fp32_peak.value if fp32_peak.value else None, "traffic": None,

@@ -7,6 +7,7 @@
 // RT_ERR_NO_DEVICE.
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -28,6 +29,8 @@ using namespace rtd;
         }                                                                                                  \
     } while (0)
 
+constexpr uint32_t MAX_PASSES = 64;  // light groups of the direct-lighting path
+
 struct rt_scene {
     int device = 0;
     DScene d{};
@@ -37,6 +40,13 @@ struct rt_scene {
     // per-render scratch, grown on demand
     float4 *samples = nullptr;
     size_t samples_cap = 0;
+    uint4 *primary_hits = nullptr;
+    size_t primary_cap = 0;
+    DirectState *direct_state = nullptr;  // running light sums between the passes of direct_kernel
+    size_t direct_cap = 0;
+    unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
+    uint32_t frame_serial = 0;              // base of the chain tags of the current frame
+    int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
     float4 *clouds = nullptr;  // K x M cloud points padded to float4 (one LDG.128 per light copy)
     size_t clouds_cap = 0;
     std::vector<float> clouds_host;
@@ -220,6 +230,9 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     int rc = grow(s->samples, s->samples_cap, std::max<size_t>(n_samples, 1) * sizeof(float4));
     if (rc) return rc;
     p.samples = s->samples;
+    rc = grow(s->primary_hits, s->primary_cap, std::max<size_t>(p.n_items, 1) * sizeof(uint4));
+    if (rc) return rc;
+    p.primary_hits = s->primary_hits;
     p.work_counter = s->work_counter;
     p.counters = s->counters;
     if (p.local_rows == 0) return RT_OK;
@@ -230,15 +243,59 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     uint32_t warps_needed = (p.n_items + 31) / 32;
     grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, (warps_needed + CTA_WARPS - 1) / CTA_WARPS));
     p.tail_div = 2u * (uint32_t)grid * CTA_WARPS;
+    if (const char *e = getenv("RT_TAIL_DIV")) p.tail_div = (uint32_t)std::max(1, atoi(e));  // tuning experiments
+    const unsigned pgrid = (p.n_items + 127u) / 128u;
+    const bool bounces = (cfg->flags & (RT_FLAG_REFLECTIONS | RT_FLAG_REFRACTIONS)) != 0;
     if (count)
-        render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
+        primary_kernel<true><<<pgrid, 128, 0, stream>>>(p);
     else
-        render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
+        primary_kernel<false><<<pgrid, 128, 0, stream>>>(p);
     CU_CHECK(cudaGetLastError());
+    if (launches) *launches += 1;
+    if (bounces) {
+        // per-sample reflection / refraction trees: persistent megakernel
+        if (count)
+            render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
+        else
+            render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
+        CU_CHECK(cudaGetLastError());
+        if (launches) *launches += 1;
+    } else {
+        // direct lighting only: one pass per light group over all samples
+        const uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);
+        const uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
+        if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
+        {
+            const size_t before = s->direct_cap;
+            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>(p.n_items, 1) * sizeof(DirectState));
+            if (rc) return rc;
+            if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
+        }
+        CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
+        int dgrid = s->sm_count * (count ? s->ctas_per_sm_direct_count : s->ctas_per_sm_direct);
+        dgrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)dgrid, (warps_needed * passes + CTA_WARPS - 1) / CTA_WARPS));
+        RenderParams pd = p;
+        if (n_groups == 0) {  // no lights: ambient term only
+            pd.LM = 0;
+            pd.M = 1;
+        }
+        // tags of this frame's chained records: never equal to a tag left in the buffer by an earlier frame
+        s->frame_serial += MAX_PASSES;
+        if (s->frame_serial > 0xFFFF0000u) {
+            CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
+            s->frame_serial = MAX_PASSES;
+        }
+        if (count)
+            direct_kernel<true><<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
+        else
+            direct_kernel<false><<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
+        CU_CHECK(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
     uint32_t n_pix = p.local_rows * p.width;
     resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask);
     CU_CHECK(cudaGetLastError());
-    if (launches) *launches += 2;
+    if (launches) *launches += 1;
     return RT_OK;
 }
 
@@ -347,7 +404,11 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
         s->ctas_per_sm_count = 1;
-    if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
+        s->ctas_per_sm_direct = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
+        s->ctas_per_sm_direct_count = 1;
+    if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
         cudaEventCreate(&s->ev1) != cudaSuccess)
         return fail(rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -358,7 +419,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->clouds, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->clouds, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);

@@ -49,6 +49,7 @@ struct RenderParams {
     uint32_t tiles_x, n_items;
     uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
+    uint4 *primary_hits;           // n_items: closest hit of every primary sample (primary_kernel): bits t, slot, prim, meta
     unsigned int *work_counter;
     unsigned long long *counters;  // closest, shadow, box, tri, sph
 };
@@ -66,6 +67,90 @@ RT_DEV uint32_t tile_image_row(const RenderParams &p, uint32_t local_row) {
     if (p.tile_world <= 1 || p.tile_rows == 0) return local_row;
     uint32_t t = local_row / p.tile_rows, r = local_row - t * p.tile_rows;
     return (t * p.tile_world + p.tile_rank) * p.tile_rows + r;
+}
+
+// Work item -> pixel and sample. Items are ordered in 8x4-pixel tiles of the rank's local image,
+// samples innermost, so the 32 items of a warp are 2 neighbouring pixels x 16 samples (coherent).
+struct ItemInfo {
+    bool valid;
+    uint32_t x, ly, s;
+};
+RT_DEV ItemInfo decode_item(const RenderParams &p, uint32_t item) {
+    ItemInfo it;
+    uint32_t pix = item / p.S;
+    it.s = item - pix * p.S;
+    uint32_t tile = pix / (TILE_W * TILE_H), within = pix - tile * (TILE_W * TILE_H);
+    uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+    it.x = tx * TILE_W + (within % TILE_W);
+    it.ly = ty * TILE_H + (within / TILE_W);
+    it.valid = item < p.n_items && it.x < p.width && it.ly < p.local_rows;
+    return it;
+}
+
+// get_pixel_color / render_pixel_colors (raytracer_renderer.rs:1140-1357): origin on the z = 0 plane
+// (+ AA offset), direction = pixel centre - focus (un-normalised; Ray::new normalises)
+RT_DEV void primary_ray(const RenderParams &p, uint32_t pix_x, uint32_t pix_y, uint32_t s, float3 &o, float3 &dir) {
+    float cx = (float)pix_x * p.w2s_w, cy = (float)pix_y * p.w2s_h;
+    dir = f3(cx, cy, 0.0f) - f3(p.focus_x, p.focus_y, p.focus_z);
+    o = f3(cx + p.aa_off[2 * s], cy + p.aa_off[2 * s + 1], 0.0f);
+}
+
+// One (shading point, light copy) pair: the body of the `for light in lights` loop of
+// calculate_lighting (raytracer_renderer.rs:773-870) with PointLight::to_point_light_cloud
+// (light.rs:183-225), the shadow query and PointLight::calculate_contribution_at (light.rs:261-299).
+// Returns the diffuse and specular terms this light copy adds (zero when occluded / facing away).
+template <bool COUNT>
+RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, uint32_t li, uint32_t cpy,
+                       uint32_t cloud, bool cull, Counters &cn, float3 &dc, float3 &spc) {
+    const DScene &sc = p.sc;
+    dc = splat(0.0f);
+    spc = splat(0.0f);
+    const float4 l0 = __ldg(sc.lights + 2 * li), l1 = __ldg(sc.lights + 2 * li + 1);
+    float3 lpos = f3(l0.x, l0.y, l0.z);
+    float lint = l0.w;
+    const float3 lcol = f3(l1.x, l1.y, l1.z);
+    if (p.M > 1) {
+        const float4 cp = __ldg(p.clouds + (size_t)cloud * p.M + cpy);
+        float3 rp = f3(cp.x, cp.y, cp.z);
+        lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
+        lint = p.inv_M * lint;
+    }
+    const float3 l2p = lpos - hp;
+    const float3 ldir = normalized3(l2p);
+    const float3 q = hp + ldir * p.eps_d;
+    const float maxd = mag3(lpos - q);
+    const ShadowResult sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
+    // Everything below only matters when the light is unoccluded AND the surface faces it
+    // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
+    const float diffuse = smax(dot3(hn, ldir), 0.0f);
+    if (sh.occluded || !(diffuse > 0.0f)) return;
+    const float ldist = mag3(l2p) + EPS;
+    const float cosi = dot3(l2p, hn) / ldist;
+    if (cosi > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
+        const float att = 0.95f * (EPS + ldist + ldist * ldist);
+        const float sig = (tanhf(att) + 1.0f) / 2.0f;
+        const float cint = cosi * lint * sclamp(sig, 0.0f, 1.0f);
+        const float3 ccolor = mcolor * lcol;
+        // colour / filter; x / 1.0f == x exactly, and the filter is (1,1,1) unless the ray crossed a
+        // transmissive primitive
+        const bool unit_filter = sh.filter.x == 1.0f && sh.filter.y == 1.0f && sh.filter.z == 1.0f;
+        const float3 lcs = unit_filter ? ccolor : ccolor / sh.filter;
+        float spec = 0.0f;
+        const bool has_spec = mshininess > 0.0f;
+        if (has_spec) {
+            float3 rr = reflected3(ldir, hn);
+            float sd = smax(dot3(normalized3(rr), view), 0.0f);
+            spec = powf(sd, smax(mshininess * 512.0f, 1.0f));
+        }
+        const float lf = diffuse * cint * sh.opacity;
+        const float sf = cint * sh.opacity * spec;
+        dc = mcolor * lcs * lf;
+        if (has_spec) spc = lcol * sf;
+    } else {
+        // cosi <= 0 with diffuse > 0 (rounding only): contribution colour and intensity are zero; the
+        // specular term is l.color * (0 * opacity * spec) = 0 exactly.
+        dc = mcolor * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
+    }
 }
 
 struct PathRec {  // one pending ray of a sample's reflection/refraction tree (48 B)
@@ -97,7 +182,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
     PathRec stack[PATH_STACK];
     int sp = 0;
     bool have_item = false, have_ray = false;
-    uint32_t sample_index = 0, pix_x = 0, pix_y = 0;
+    uint32_t sample_index = 0, item_index = 0, pix_x = 0, pix_y = 0;
     float3 acc = splat(0.0f);
     bool sample_valid = false;
     // current ray
@@ -144,30 +229,22 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
                 grant = __shfl_sync(FULL, grant, leader);
                 const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
                 const uint32_t item = base + rank;
-                if (need && rank < grant && item < p.n_items) {
-                    uint32_t pix = item / p.S, s = item - pix * p.S;
-                    uint32_t tile = pix / (TILE_W * TILE_H), within = pix - tile * (TILE_W * TILE_H);
-                    uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-                    uint32_t x = tx * TILE_W + (within % TILE_W), ly = ty * TILE_H + (within / TILE_W);
-                    if (x < p.width && ly < p.local_rows) {
-                        pix_x = x;
-                        pix_y = tile_image_row(p, ly);
-                        sample_index = (ly * p.width + x) * p.S + s;
-                        // get_pixel_color / render_pixel_colors (raytracer_renderer.rs:1140-1357)
-                        float cx = (float)pix_x * p.w2s_w, cy = (float)pix_y * p.w2s_h;
-                        float3 dir = f3(cx, cy, 0.0f) - f3(p.focus_x, p.focus_y, p.focus_z);
-                        ro = f3(cx + p.aa_off[2 * s], cy + p.aa_off[2 * s + 1], 0.0f);
-                        rd = dir;
-                        rw = splat(1.0f);
-                        r_ior = AIR_IOR;
-                        r_depth = -1;
-                        r_refl_child = false;
-                        r_primary = true;
-                        acc = splat(0.0f);
-                        sample_valid = false;
-                        have_item = true;
-                        have_ray = true;
-                    }
+                const ItemInfo it = decode_item(p, item);
+                if (need && rank < grant && it.valid) {
+                    pix_x = it.x;
+                    pix_y = tile_image_row(p, it.ly);
+                    sample_index = (it.ly * p.width + it.x) * p.S + it.s;
+                    item_index = item;
+                    primary_ray(p, pix_x, pix_y, it.s, ro, rd);
+                    rw = splat(1.0f);
+                    r_ior = AIR_IOR;
+                    r_depth = -1;
+                    r_refl_child = false;
+                    r_primary = true;
+                    acc = splat(0.0f);
+                    sample_valid = false;
+                    have_item = true;
+                    have_ray = true;
                 }
             }
         }
@@ -182,7 +259,16 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
         h.prim = 0;
         if (have_ray) {
             d = normalized3(rd);  // Ray::new_with_mask (ray.rs:52-57)
-            h = trace_closest<COUNT>(sc, ro, d, cull, cn);
+            if (r_primary) {  // traced by primary_kernel at full width; here only fetched
+                const uint4 ph = p.primary_hits[item_index];
+                h.t = __uint_as_float(ph.x);
+                h.slot = (int32_t)ph.y;
+                h.prim = ph.z;
+                h.meta = ph.w;
+                if (COUNT) cn.closest++;
+            } else {
+                h = trace_closest<COUNT>(sc, ro, d, cull, cn);
+            }
         }
         const bool hit = have_ray && h.slot >= 0;
         if (hit) {
@@ -240,58 +326,11 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
                     li = l / p.M;
                     cpy = l - li * p.M;
                 }
-                const float4 l0 = __ldg(sc.lights + 2 * li), l1 = __ldg(sc.lights + 2 * li + 1);
-                float3 lpos = f3(l0.x, l0.y, l0.z);
-                float lint = l0.w;
-                const float3 lcol = f3(l1.x, l1.y, l1.z);
-                if (p.M > 1) {
-                    uint32_t ci = li < MAX_SM_LIGHTS
-                                      ? ws.cloud[s][li]
-                                      : cloud_index(p.seed, packet_noaa ? __float_as_uint(r2.z) / 8u : __float_as_uint(r2.z), __float_as_uint(r2.w), li, p.K);
-                    const float4 cp = __ldg(p.clouds + (size_t)ci * p.M + cpy);
-                    float3 rp = f3(cp.x, cp.y, cp.z);
-                    lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
-                    lint = p.inv_M * lint;
-                }
-                // calculate_lighting body (raytracer_renderer.rs:773-870)
-                const float3 l2p = lpos - hp;
-                const float3 ldir = normalized3(l2p);
-                const float3 q = hp + ldir * p.eps_d;
-                const float maxd = mag3(lpos - q);
-                const ShadowResult sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
-                // Everything below only matters when the light is unoccluded AND the surface faces it
-                // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
-                const float diffuse = smax(dot3(hn, ldir), 0.0f);
-                if (!sh.occluded && diffuse > 0.0f) {
-                    // PointLight::calculate_contribution_at (light.rs:261-299)
-                    const float ldist = mag3(l2p) + EPS;
-                    const float cosi = dot3(l2p, hn) / ldist;
-                    if (cosi > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
-                        const float att = 0.95f * (EPS + ldist + ldist * ldist);
-                        const float sig = (tanhf(att) + 1.0f) / 2.0f;
-                        const float cint = cosi * lint * sclamp(sig, 0.0f, 1.0f);
-                        const float3 ccolor = mcolor * lcol;
-                        // colour / filter; x / 1.0f == x exactly, and the filter is (1,1,1) unless the
-                        // ray crossed a transmissive primitive
-                        const bool unit_filter = sh.filter.x == 1.0f && sh.filter.y == 1.0f && sh.filter.z == 1.0f;
-                        const float3 lcs = unit_filter ? ccolor : ccolor / sh.filter;
-                        float spec = 0.0f;
-                        const bool has_spec = mshininess > 0.0f;
-                        if (has_spec) {
-                            float3 rr = reflected3(ldir, hn);
-                            float sd = smax(dot3(normalized3(rr), view), 0.0f);
-                            spec = powf(sd, smax(mshininess * 512.0f, 1.0f));
-                        }
-                        const float lf = diffuse * cint * sh.opacity;
-                        const float sf = cint * sh.opacity * spec;
-                        dc = mcolor * lcs * lf;
-                        if (has_spec) spc = lcol * sf;
-                    } else {
-                        // cosi <= 0 with diffuse > 0 (rounding only): contribution colour and intensity
-                        // are zero; the specular term is l.color * (0 * opacity * spec) = 0 exactly.
-                        dc = mcolor * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
-                    }
-                }
+                const uint32_t ci = p.M > 1 ? (li < MAX_SM_LIGHTS ? ws.cloud[s][li]
+                                                                   : cloud_index(p.seed, packet_noaa ? __float_as_uint(r2.z) / 8u : __float_as_uint(r2.z),
+                                                                                 __float_as_uint(r2.w), li, p.K))
+                                            : 0u;
+                shade_pair<COUNT>(p, hp, hn, view, mcolor, mshininess, li, cpy, ci, cull, cn, dc, spc);
             }
             if (n_live == 32) {
                 sum_d = sum_d + dc;  // pair (l, s = lane): this lane's own hit, next light in order
@@ -391,6 +430,142 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
         __syncwarp();
     }
 
+    if (COUNT) {
+        atomicAdd(p.counters + 0, cn.closest);
+        atomicAdd(p.counters + 1, cn.shadow);
+        atomicAdd(p.counters + 2, cn.box);
+        atomicAdd(p.counters + 3, cn.tri);
+        atomicAdd(p.counters + 4, cn.sph);
+    }
+}
+
+// Closest hit of every primary sample, one thread per work item (same item order as render_kernel).
+// Splitting this off keeps the divergent closest-hit traversal at full warp width and lets
+// render_kernel fetch work in small chunks (fine-grained load balance) at no cost.
+template <bool COUNT>
+__global__ void __launch_bounds__(128) primary_kernel(const RenderParams p) {
+    const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+    const ItemInfo it = decode_item(p, item);
+    if (!it.valid) return;
+    Counters cn = {0, 0, 0, 0, 0};
+    float3 o, dir;
+    primary_ray(p, it.x, tile_image_row(p, it.ly), it.s, o, dir);
+    const ClosestHit h = trace_closest<COUNT>(p.sc, o, normalized3(dir), (p.flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);
+    p.primary_hits[item] = make_uint4(__float_as_uint(h.t), (uint32_t)h.slot, h.prim, h.meta);
+    if (COUNT) {  // rays are counted where they are consumed (render_kernel); tests are counted here
+        atomicAdd(p.counters + 2, cn.box);
+        atomicAdd(p.counters + 3, cn.tri);
+        atomicAdd(p.counters + 4, cn.sph);
+    }
+}
+
+// Direct lighting without bounces (no `reflections` / `refractions` feature): every sample is one
+// primary hit + its L*M shadow rays, so the frame is processed as a stream of small, uniform work
+// units instead of per-sample trees.  Unit = (batch of 32 neighbouring samples, light group), a
+// group being the M soft-shadow copies of one light (or all lights when M == 1).  Persistent warps
+// fetch units in light-major order with one atomicAdd each; each lane shades its own sample against
+// the group's light copies IN ORDER, continuing the running per-sample sums left by the unit of
+// the previous group -- the reference's `for light in lights` order.  Units of one batch are
+// chained through a tagged 2 x 16-byte record in global memory (the tag travels inside each
+// 16-byte store, so no fence -- and no L1 invalidation -- is needed); the predecessor was handed
+// out a whole group earlier, so the consumer practically never waits.  19 shadow batches per unit
+// instead of 95 and a single tail per frame is what keeps 8-GPU strong scaling efficient.
+struct DirectState {  // running light sums of one sample: (sum.rgb, bits tag) twice
+    float4 d, s;
+};
+// gpu-scope relaxed 16-byte accesses for the chained records (volatile asm: the spin loop must
+// really re-load, and the compiler may not assume the memory is unchanged)
+RT_DEV float4 ld_relaxed_gpu(const float4 *ptr) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+RT_DEV void st_relaxed_gpu(float4 *ptr, float4 v) {
+    asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
+                                                                                    unsigned int *counter, DirectState *state) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const DScene &sc = p.sc;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
+    const uint32_t n_batches = (p.n_items + 31u) / 32u;
+    const uint32_t n_units = n_batches * n_groups;
+    Counters cn = {0, 0, 0, 0, 0};
+    for (;;) {
+        uint32_t unit = 0;
+        if (lane == 0) unit = atomicAdd(counter, 1u);
+        unit = __shfl_sync(FULL, unit, 0);
+        if (unit >= n_units) break;
+        const uint32_t group_index = unit / n_batches, batch = unit - group_index * n_batches;
+        const bool last = group_index + 1 == n_groups;
+        const uint32_t item = batch * 32u + lane;
+        const ItemInfo it = decode_item(p, item);
+        uint4 ph = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+        if (it.valid) ph = p.primary_hits[item];
+        const bool hit = it.valid && (int32_t)ph.y >= 0;
+        const uint32_t sample_index = (it.ly * p.width + it.x) * p.S + it.s;
+        if (COUNT && it.valid && group_index == 0) cn.closest++;
+        if (!hit) {
+            if (it.valid && last) p.samples[sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            continue;  // lanes of a batch that missed simply sit this batch out
+        }
+        // rebuild the hit record of this lane's sample (cheap next to its shadow rays)
+        const uint32_t pix_x = it.x, pix_y = tile_image_row(p, it.ly);
+        float3 o, dir;
+        primary_ray(p, pix_x, pix_y, it.s, o, dir);
+        const float3 d = normalized3(dir);
+        const float t = __uint_as_float(ph.x);
+        const int32_t slot = (int32_t)ph.y;
+        const uint32_t meta = ph.w;
+        const float3 P = ray_at(o, d, t);
+        float3 N;
+        if (meta & rtb::PRIM_SPHERE) {
+            const float4 q0 = __ldg(sc.prims + 4 * (size_t)slot);
+            N = normalized3(P - f3(q0.x, q0.y, q0.z));
+        } else {
+            const float4 sn = __ldg(sc.shade_n + slot);
+            N = f3(sn.x, sn.y, sn.z);
+        }
+        const Material m = load_material(sc, meta & rtb::PRIM_MATERIAL_MASK);
+        float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
+        if (group_index > 0) {
+            // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
+            const uint32_t want = frame_tag + group_index - 1u;
+            float4 sd, ss;
+            do {
+                sd = ld_relaxed_gpu(&state[item].d);
+                ss = ld_relaxed_gpu(&state[item].s);
+            } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
+            sum_d = f3(sd.x, sd.y, sd.z);
+            sum_s = f3(ss.x, ss.y, ss.z);
+        }
+        const uint32_t li0 = p.M > 1 ? group_index : 0u;
+        const uint32_t cloud = p.M > 1 ? cloud_index(p.seed, packet_noaa ? pix_x / 8u : pix_x, pix_y, li0, p.K) : 0u;
+        const uint32_t n_in_group = p.M > 1 ? p.M : p.LM;
+        for (uint32_t l = 0; l < n_in_group; l++) {
+            float3 dc, spc;
+            shade_pair<COUNT>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc);
+            sum_d = sum_d + dc;
+            sum_s = sum_s + spc;
+        }
+        if (!last) {
+            const float tag = __uint_as_float(frame_tag + group_index);
+            st_relaxed_gpu(&state[item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+            st_relaxed_gpu(&state[item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+        } else {
+            // single_raytrace without bounces (raytracer_renderer.rs:195-257)
+            const float3 ambient = (m.color * splat(1.0f)) * 0.08f;
+            const float df = attenuation(t);
+            const float3 direct = (ambient + sum_d) * df;
+            const float3 specular = sum_s * df;
+            const float3 local = m.transmissive ? specular : (direct + specular);
+            p.samples[sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+        }
+    }
     if (COUNT) {
         atomicAdd(p.counters + 0, cn.closest);
         atomicAdd(p.counters + 1, cn.shadow);

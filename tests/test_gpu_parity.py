@@ -288,7 +288,7 @@ def test_renderer_api_mirror(pkg, oracle_mod):
     r = pkg.RaytracerRenderer("backface_culling", seed=0)
     buf = pkg.ImageBuffer(768, 640)
     stats = r.render(buf, scene)
-    assert stats["kernel_launches"] == 2 and stats["kernel_ms"] > 0
+    assert stats["kernel_launches"] == 3 and stats["kernel_ms"] > 0
     flat = scene.flatten()
     o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), r.config.cfg, oracle_mod.BVH)
     assert_image_parity(buf, o_argb, o_mask)
