@@ -47,9 +47,8 @@ struct rt_scene {
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
-    float4 *clouds = nullptr;  // K x M cloud points padded to float4 (one LDG.128 per light copy)
+    float *clouds = nullptr;  // K x M x 3 cloud points, as handed over
     size_t clouds_cap = 0;
-    std::vector<float> clouds_host;
     uint32_t clouds_epoch = 0, clouds_k = 0, clouds_m = 0;  // what the device copy currently holds
     const float *clouds_src = nullptr;
     unsigned int *work_counter = nullptr;
@@ -209,16 +208,9 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
                             cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && s->clouds;
         if (!cached) {
-            int rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4));
+            int rc = grow(s->clouds, s->clouds_cap, n_pts * 3 * sizeof(float));
             if (rc) return rc;
-            s->clouds_host.resize(4 * n_pts);
-            for (size_t i = 0; i < n_pts; i++) {
-                s->clouds_host[4 * i] = cfg->light_clouds[3 * i];
-                s->clouds_host[4 * i + 1] = cfg->light_clouds[3 * i + 1];
-                s->clouds_host[4 * i + 2] = cfg->light_clouds[3 * i + 2];
-                s->clouds_host[4 * i + 3] = 0.0f;
-            }
-            CU_CHECK(cudaMemcpyAsync(s->clouds, s->clouds_host.data(), n_pts * sizeof(float4), cudaMemcpyHostToDevice, stream));
+            CU_CHECK(cudaMemcpyAsync(s->clouds, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
             s->clouds_epoch = cfg->tables_epoch;
             s->clouds_src = cfg->light_clouds;
             s->clouds_k = cfg->n_light_clouds;

@@ -41,7 +41,7 @@ struct RenderParams {
     float eps_d;           // default_epsilon_distance component (vector.rs:697-700)
     float aa_off[2 * MAX_AA];
     float sample_scale;    // 1 / S
-    const float4 *clouds;  // K x M points, padded to float4
+    const float *clouds;   // K x M x 3
     uint32_t K;
     unsigned long long seed;
     uint32_t refl_depth, refr_depth;
@@ -110,8 +110,8 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     float lint = l0.w;
     const float3 lcol = f3(l1.x, l1.y, l1.z);
     if (p.M > 1) {
-        const float4 cp = __ldg(p.clouds + (size_t)cloud * p.M + cpy);
-        float3 rp = f3(cp.x, cp.y, cp.z);
+        const float *cp = p.clouds + ((size_t)cloud * p.M + cpy) * 3;
+        float3 rp = f3(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2));
         lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
         lint = p.inv_M * lint;
     }

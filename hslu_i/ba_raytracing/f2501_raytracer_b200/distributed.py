@@ -16,7 +16,7 @@ import ctypes as C
 from . import _lib as L
 from .renderer import DeviceScene, RenderConfig
 
-DEFAULT_TILE_ROWS = 2
+DEFAULT_TILE_ROWS = 8
 
 
 def padded_rows(rc: RenderConfig, tile_rows: int, world: int) -> int:
