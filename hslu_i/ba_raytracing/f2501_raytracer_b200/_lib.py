@@ -30,6 +30,7 @@ FLAG_BACKFACE_CULLING = 1 << 4
 FLAG_PACKET_SEMANTICS = 1 << 5
 FLAG_COUNT_WORK = 1 << 6
 FLAG_ZERO_MISSES = 1 << 7
+FLAG_PER_RAY_SHADOWS = 1 << 8
 
 # numpy dtypes byte-compatible with the C structs
 MATERIAL_DTYPE = np.dtype(

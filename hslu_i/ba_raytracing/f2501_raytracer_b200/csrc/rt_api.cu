@@ -50,6 +50,7 @@ struct rt_scene {
     float *clouds = nullptr;  // K x M x 3 cloud points, as handed over
     size_t clouds_cap = 0;
     uint32_t clouds_epoch = 0, clouds_k = 0, clouds_m = 0;  // what the device copy currently holds
+    float cloud_lo[3] = {0, 0, 0}, cloud_hi[3] = {0, 0, 0};  // bounds of the points in it
     const float *clouds_src = nullptr;
     unsigned int *work_counter = nullptr;
     unsigned long long *counters = nullptr;
@@ -211,12 +212,27 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             int rc = grow(s->clouds, s->clouds_cap, n_pts * 3 * sizeof(float));
             if (rc) return rc;
             CU_CHECK(cudaMemcpyAsync(s->clouds, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            for (int k = 0; k < 3; k++) {
+                float lo = INFINITY, hi = -INFINITY;
+                for (size_t i = 0; i < n_pts; i++) {
+                    const float v = cfg->light_clouds[3 * i + k];
+                    if (!std::isfinite(v)) lo = -INFINITY, hi = INFINITY;  // no usable bound: beams are switched off
+                    lo = std::min(lo, v);
+                    hi = std::max(hi, v);
+                }
+                s->cloud_lo[k] = lo;
+                s->cloud_hi[k] = hi;
+            }
             s->clouds_epoch = cfg->tables_epoch;
             s->clouds_src = cfg->light_clouds;
             s->clouds_k = cfg->n_light_clouds;
             s->clouds_m = p.M;
         }
         p.clouds = s->clouds;
+        for (int k = 0; k < 3; k++) {
+            p.cloud_lo[k] = s->cloud_lo[k];
+            p.cloud_hi[k] = s->cloud_hi[k];
+        }
     }
     size_t n_samples = (size_t)p.local_rows * p.width * p.S;
     int rc = grow(s->samples, s->samples_cap, std::max<size_t>(n_samples, 1) * sizeof(float4));
@@ -387,6 +403,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     s->d.n_lights = flat.n_lights;
     s->d.nan_hit_slot = flat.nan_hit_slot;
     s->d.nan_hit_slot_culled = flat.nan_hit_slot_culled;
+    s->d.box_pad = flat.box_pad;
     s->n_nodes = flat.n_nodes;
     s->n_prims = flat.n_prims;
     cudaDeviceProp prop;

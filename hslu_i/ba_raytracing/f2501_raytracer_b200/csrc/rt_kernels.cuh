@@ -42,6 +42,7 @@ struct RenderParams {
     float aa_off[2 * MAX_AA];
     float sample_scale;    // 1 / S
     const float *clouds;   // K x M x 3
+    float cloud_lo[3], cloud_hi[3];  // component-wise bounds of all cloud points (shadow beams)
     uint32_t K;
     unsigned long long seed;
     uint32_t refl_depth, refr_depth;
@@ -99,9 +100,12 @@ RT_DEV void primary_ray(const RenderParams &p, uint32_t pix_x, uint32_t pix_y, u
 // calculate_lighting (raytracer_renderer.rs:773-870) with PointLight::to_point_light_cloud
 // (light.rs:183-225), the shadow query and PointLight::calculate_contribution_at (light.rs:261-299).
 // Returns the diffuse and specular terms this light copy adds (zero when occluded / facing away).
+// `cand` / `n_cand` (>= 0): the beam's candidate list for this (shading point, light), see beam_collect;
+// n_cand < 0: the shadow query walks the BVH itself.
 template <bool COUNT>
 RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, uint32_t li, uint32_t cpy,
-                       uint32_t cloud, bool cull, Counters &cn, float3 &dc, float3 &spc) {
+                       uint32_t cloud, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
+                       int32_t *last_occluder = nullptr) {
     const DScene &sc = p.sc;
     dc = splat(0.0f);
     spc = splat(0.0f);
@@ -119,7 +123,8 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const float3 ldir = normalized3(l2p);
     const float3 q = hp + ldir * p.eps_d;
     const float maxd = mag3(lpos - q);
-    const ShadowResult sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
+    const ShadowResult sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, normalized3(ldir), maxd, cull, cn)
+                                        : trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
     const float diffuse = smax(dot3(hn, ldir), 0.0f);
@@ -546,9 +551,24 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         const uint32_t li0 = p.M > 1 ? group_index : 0u;
         const uint32_t cloud = p.M > 1 ? cloud_index(p.seed, packet_noaa ? pix_x / 8u : pix_x, pix_y, li0, p.K) : 0u;
         const uint32_t n_in_group = p.M > 1 ? p.M : p.LM;
+        // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
+        uint32_t cand[BEAM_MAX_CAND];
+        int n_cand = -1;
+        int32_t last_occluder = -1;
+        if (p.M > 1 && !(p.flags & RT_FLAG_PER_RAY_SHADOWS) && p.cloud_hi[0] - p.cloud_lo[0] < 3.0e38f && p.cloud_hi[1] - p.cloud_lo[1] < 3.0e38f &&
+            p.cloud_hi[2] - p.cloud_lo[2] < 3.0e38f) {
+            const float4 l0 = __ldg(sc.lights + 2 * li0);
+            const float3 lpos = f3(l0.x, l0.y, l0.z), w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
+            // the same float operations as shade_pair's `lpos + rp * w2s`, which are monotonic in rp
+            const float3 lmin = lpos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
+            const float3 lmax = lpos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
+            const Beam beam = make_beam(P, lmin, lmax, 0.25f * sc.box_pad);
+            n_cand = beam_collect<COUNT>(sc, beam, cand, cn);
+        }
         for (uint32_t l = 0; l < n_in_group; l++) {
             float3 dc, spc;
-            shade_pair<COUNT>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc);
+            shade_pair<COUNT>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc, cand, n_cand,
+                              &last_occluder);
             sum_d = sum_d + dc;
             sum_s = sum_s + spc;
         }

@@ -102,7 +102,10 @@ enum {
     RT_FLAG_BACKFACE_CULLING = 1u << 4,         /* feature backface_culling (per-ray term) */
     RT_FLAG_PACKET_SEMANTICS = 1u << 5,         /* feature simd_render: AA pattern + cloud sharing */
     RT_FLAG_COUNT_WORK = 1u << 6,               /* run the counter build (untimed; fills rt_stats counts) */
-    RT_FLAG_ZERO_MISSES = 1u << 7               /* write 0 for miss pixels instead of leaving them */
+    RT_FLAG_ZERO_MISSES = 1u << 7,              /* write 0 for miss pixels instead of leaving them */
+    RT_FLAG_PER_RAY_SHADOWS = 1u << 8           /* every shadow query walks the BVH itself (no shadow beams):
+                                                   same image bit for bit; the counter build of this mode gives
+                                                   the canonical per-ray test counts of the roofline */
 };
 
 typedef struct rt_config {
