@@ -67,7 +67,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("box_tests", C.c_uint64), ("triangle_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
-        ("kernel_launches", C.c_uint64),
+        ("kernel_launches", C.c_uint64), ("beam_triangle_tests", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:

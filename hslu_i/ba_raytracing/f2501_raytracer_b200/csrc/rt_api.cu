@@ -315,6 +315,7 @@ static int fetch_counters(rt_scene *s, rt_stats *st) {
     st->box_tests = c[2];
     st->triangle_tests = c[3];
     st->sphere_tests = c[4];
+    st->beam_triangle_tests = c[5];
     return RT_OK;
 }
 
@@ -364,6 +365,16 @@ int rt_measure_fp32_peak(int device, double *out_tflops) {
     *out_tflops = best;
     return RT_OK;
 }
+
+#ifdef RT_DBG_REJECT
+int rt_dbg_counters(unsigned long long *out8) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, rtd::g_dbg, sizeof(z));
+    cudaMemcpyToSymbol(rtd::g_dbg, z, sizeof(z));
+    return 0;
+}
+#endif
 
 int rt_device_count(void) {
     int n = 0;

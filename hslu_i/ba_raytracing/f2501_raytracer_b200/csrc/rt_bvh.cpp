@@ -433,6 +433,9 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
             q[12] = u2f(p);
             q[13] = u2f(t.material | (transmissive[t.material] ? PRIM_TRANSMISSIVE : 0u));
             q[14] = u2f(ref_tag[b.order[slot]]);
+            float emax = 0.0f;
+            for (int k = 0; k < 3; k++) emax = std::max(emax, std::max(std::fabs(e1[k]), std::fabs(e2[k])));
+            q[15] = 64.0f * 1.1920929e-7f * emax;  // error bound factor of tri_test's early-out (rt_device.cuh)
             float *sn = &out.shade_n[4 * (size_t)slot];
             sn[0] = t.normal[0]; sn[1] = t.normal[1]; sn[2] = t.normal[2];
             if (p < best_any) {

@@ -20,7 +20,7 @@ namespace rtb {
 //             q2 = (e2.z, g.x, g.y, g.z)  with g = cross(e1, e2) (the first row of the inverse,
 //                  identical bit for bit to cross(-e1, -e2) evaluated per ray)
 //   sphere:   q0 = (c.x, c.y, c.z, r*r)      q1, q2 unused
-//   both:     q3 = (bits(prim_index), bits(meta), bits(cell), 0)
+//   both:     q3 = (bits(prim_index), bits(meta), bits(cell), triangle: 64 eps * max|edge component|)
 //             meta = material index | PRIM_TRANSMISSIVE | PRIM_SPHERE
 //             cell = 0, or TRI_CELL(k, i, j, upper) when the slot is one cell of a large triangle
 //                    that is referenced once per cell of a k x k barycentric subdivision

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
     const bool refl_on = (p.flags & RT_FLAG_REFLECTIONS) != 0;
     const bool refr_on = (p.flags & RT_FLAG_REFRACTIONS) != 0;
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0, 0};
 
     PathRec stack[PATH_STACK];
     int sp = 0;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(128) primary_kernel(const RenderParams p) {
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     const ItemInfo it = decode_item(p, item);
     if (!it.valid) return;
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0, 0};
     float3 o, dir;
     primary_ray(p, it.x, tile_image_row(p, it.ly), it.s, o, dir);
     const ClosestHit h = trace_closest<COUNT>(p.sc, o, normalized3(dir), (p.flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0, 0};
     for (;;) {
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
@@ -562,8 +562,13 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
             // the same float operations as shade_pair's `lpos + rp * w2s`, which are monotonic in rp
             const float3 lmin = lpos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
             const float3 lmax = lpos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
-            const Beam beam = make_beam(P, lmin, lmax, 0.25f * sc.box_pad);
+            const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
+            const Beam beam = make_beam(P, lmin, lmax, pad);
             n_cand = beam_collect<COUNT>(sc, beam, cand, cn);
+            if (n_cand > 0) {
+                const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
+                n_cand = beam_filter<COUNT>(sc, P, C - P, hh, cand, n_cand, cn);
+            }
         }
         for (uint32_t l = 0; l < n_in_group; l++) {
             float3 dc, spc;
@@ -592,6 +597,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         atomicAdd(p.counters + 2, cn.box);
         atomicAdd(p.counters + 3, cn.tri);
         atomicAdd(p.counters + 4, cn.sph);
+        atomicAdd(p.counters + 5, cn.beam_prim);
     }
 }
 
@@ -639,7 +645,7 @@ __global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_
 __global__ void trace_closest_kernel(DScene sc, uint32_t flags, const float *__restrict__ rays, uint32_t n, float *out_t, uint32_t *out_prim) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0, 0};
     float3 o = f3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
     float3 d = normalized3(f3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
     ClosestHit h = trace_closest<false>(sc, o, d, (flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);
@@ -651,7 +657,7 @@ __global__ void trace_shadow_kernel(DScene sc, uint32_t flags, const float *__re
                                     float *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Counters cn = {0, 0, 0, 0, 0};
+    Counters cn = {0, 0, 0, 0, 0, 0};
     float3 o = f3(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]);
     float3 d = normalized3(f3(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]));
     ShadowResult s = trace_shadow<false>(sc, o, d, max_dist[i], (flags & RT_FLAG_BACKFACE_CULLING) != 0, cn);

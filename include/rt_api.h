@@ -144,6 +144,7 @@ typedef struct rt_stats {
     uint64_t triangle_tests;
     uint64_t sphere_tests;
     uint64_t kernel_launches; /* kernels launched by this call */
+    uint64_t beam_triangle_tests; /* shadow-beam vs triangle culling tests (one per beam, not per ray) */
 } rt_stats;
 
 typedef struct rt_scene rt_scene; /* opaque: device-resident SoA geometry + BVH */

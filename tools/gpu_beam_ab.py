@@ -26,7 +26,7 @@ for name in sys.argv[1:] or ["c3"]:
         rays = st["closest_rays"] + st["shadow_rays"]
         out[tag] = runs[0][0]
         print(f"{name}/{tag}: kernel_ms={ms:.3f} Grays/s={rays/ms/1e6:.2f} rays={rays} box/ray={st['box_tests']/rays:.2f} "
-              f"tri/ray={st['triangle_tests']/rays:.2f} sph/ray={st['sphere_tests']/rays:.3f}", flush=True)
+              f"tri/ray={st['triangle_tests']/rays:.2f} sph/ray={st['sphere_tests']/rays:.3f} beamtri/ray={st['beam_triangle_tests']/rays:.3f}", flush=True)
     same = np.array_equal(out["beam"].buffer, out["ray"].buffer) and np.array_equal(out["beam"].hit_mask, out["ray"].hit_mask)
     print(f"{name}: images identical = {same}; differing pixels = {int((out['beam'].buffer != out['ray'].buffer).sum())}", flush=True)
     dev.close()
