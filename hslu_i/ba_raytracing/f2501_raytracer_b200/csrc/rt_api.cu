@@ -293,10 +293,11 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
             s->frame_serial = MAX_PASSES;
         }
-        if (count)
-            direct_kernel<true><<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
-        else
-            direct_kernel<false><<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
+        // shadow beams need M copies per light and usable bounds of the cloud points
+        const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
+                           std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
+        auto kernel = count ? (beams ? direct_kernel<true, true> : direct_kernel<true, false>) : (beams ? direct_kernel<false, true> : direct_kernel<false, false>);
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
         CU_CHECK(cudaGetLastError());
         if (launches) *launches += 1;
     }
@@ -424,9 +425,9 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
         s->ctas_per_sm_count = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
         s->ctas_per_sm_direct = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
         s->ctas_per_sm_direct_count = 1;
     if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||

@@ -102,7 +102,8 @@ RT_DEV void primary_ray(const RenderParams &p, uint32_t pix_x, uint32_t pix_y, u
 // Returns the diffuse and specular terms this light copy adds (zero when occluded / facing away).
 // `cand` / `n_cand` (>= 0): the beam's candidate list for this (shading point, light), see beam_collect;
 // n_cand < 0: the shadow query walks the BVH itself.
-template <bool COUNT>
+// BEAM: the caller built a beam; its overflow fallback (n_cand < 0) is the out-of-line traversal.
+template <bool COUNT, bool BEAM = false>
 RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, uint32_t li, uint32_t cpy,
                        uint32_t cloud, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
                        int32_t *last_occluder = nullptr) {
@@ -123,29 +124,34 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const float3 ldir = normalized3(l2p);
     const float3 q = hp + ldir * p.eps_d;
     const float maxd = mag3(lpos - q);
-    const ShadowResult sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, normalized3(ldir), maxd, cull, cn)
-                                        : trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
+    ShadowResult sh;
+    if (BEAM)
+        sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, normalized3(ldir), maxd, cull, cn)
+                         : trace_shadow_outlined<COUNT>(sc, q, normalized3(ldir), maxd, cull, &cn);
+    else
+        sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
     const float diffuse = smax(dot3(hn, ldir), 0.0f);
     if (sh.occluded || !(diffuse > 0.0f)) return;
-    const float ldist = mag3(l2p) + EPS;
-    const float cosi = dot3(l2p, hn) / ldist;
-    if (cosi > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
+    const float ldist = sqrt_fast(dot3(l2p, l2p)) + EPS;  // from here on: colour only (fast math, rt_device.cuh)
+    const float cosn = dot3(l2p, hn);                       // cosi = cosn / ldist > 0 <=> cosn > 0 (ldist > 0)
+    if (cosn > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
+        const float cosi = cosn * rcp_fast(ldist);
         const float att = 0.95f * (EPS + ldist + ldist * ldist);
-        const float sig = (tanhf(att) + 1.0f) / 2.0f;
+        const float sig = (tanh_pos_fast(att) + 1.0f) * 0.5f;
         const float cint = cosi * lint * sclamp(sig, 0.0f, 1.0f);
         const float3 ccolor = mcolor * lcol;
         // colour / filter; x / 1.0f == x exactly, and the filter is (1,1,1) unless the ray crossed a
         // transmissive primitive
         const bool unit_filter = sh.filter.x == 1.0f && sh.filter.y == 1.0f && sh.filter.z == 1.0f;
-        const float3 lcs = unit_filter ? ccolor : ccolor / sh.filter;
+        const float3 lcs = unit_filter ? ccolor : ccolor * f3(rcp_fast(sh.filter.x), rcp_fast(sh.filter.y), rcp_fast(sh.filter.z));
         float spec = 0.0f;
         const bool has_spec = mshininess > 0.0f;
         if (has_spec) {
-            float3 rr = reflected3(ldir, hn);
-            float sd = smax(dot3(normalized3(rr), view), 0.0f);
-            spec = powf(sd, smax(mshininess * 512.0f, 1.0f));
+            const float3 rr = reflected3(ldir, hn);
+            const float sd = smax(dot3(rr, view) * rsqrt_fast(dot3(rr, rr)), 0.0f);
+            spec = pow_pos_fast(sd, smax(mshininess * 512.0f, 1.0f));
         }
         const float lf = diffuse * cint * sh.opacity;
         const float sf = cint * sh.opacity * spec;
@@ -489,7 +495,7 @@ RT_DEV void st_relaxed_gpu(float4 *ptr, float4 v) {
     asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <bool COUNT>
+template <bool COUNT, bool BEAM>
 __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
                                                                                     unsigned int *counter, DirectState *state) {
     const uint32_t lane = threadIdx.x & 31;
@@ -555,8 +561,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         uint32_t cand[BEAM_MAX_CAND];
         int n_cand = -1;
         int32_t last_occluder = -1;
-        if (p.M > 1 && !(p.flags & RT_FLAG_PER_RAY_SHADOWS) && p.cloud_hi[0] - p.cloud_lo[0] < 3.0e38f && p.cloud_hi[1] - p.cloud_lo[1] < 3.0e38f &&
-            p.cloud_hi[2] - p.cloud_lo[2] < 3.0e38f) {
+        if (BEAM) {
             const float4 l0 = __ldg(sc.lights + 2 * li0);
             const float3 lpos = f3(l0.x, l0.y, l0.z), w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
             // the same float operations as shade_pair's `lpos + rp * w2s`, which are monotonic in rp
@@ -572,8 +577,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         }
         for (uint32_t l = 0; l < n_in_group; l++) {
             float3 dc, spc;
-            shade_pair<COUNT>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc, cand, n_cand,
-                              &last_occluder);
+            shade_pair<COUNT, BEAM>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc, cand, n_cand,
+                                    &last_occluder);
             sum_d = sum_d + dc;
             sum_s = sum_s + spc;
         }
