@@ -47,9 +47,10 @@ struct rt_scene {
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
-    float *clouds = nullptr;  // K x M x 3 cloud points, as handed over
-    size_t clouds_cap = 0;
-    uint32_t clouds_epoch = 0, clouds_k = 0, clouds_m = 0;  // what the device copy currently holds
+    float *clouds_raw = nullptr;  // K x M x 3 cloud points, as handed over
+    float4 *clouds = nullptr;     // the same points scaled to scene units (scale_clouds_kernel)
+    size_t clouds_raw_cap = 0, clouds_cap = 0;
+    uint32_t clouds_epoch = 0, clouds_k = 0, clouds_m = 0, clouds_w = 0, clouds_h = 0;  // what the device copy currently holds
     float cloud_lo[3] = {0, 0, 0}, cloud_hi[3] = {0, 0, 0};  // bounds of the points in it
     const float *clouds_src = nullptr;
     unsigned int *work_counter = nullptr;
@@ -207,11 +208,16 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     if (p.LM > 0 && p.M > 1) {
         const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
         const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
-                            cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && s->clouds;
+                            cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && cfg->width == s->clouds_w && cfg->height == s->clouds_h &&
+                            s->clouds;
         if (!cached) {
-            int rc = grow(s->clouds, s->clouds_cap, n_pts * 3 * sizeof(float));
+            int rc = grow(s->clouds_raw, s->clouds_raw_cap, n_pts * 3 * sizeof(float));
             if (rc) return rc;
-            CU_CHECK(cudaMemcpyAsync(s->clouds, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            if ((rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4)))) return rc;
+            CU_CHECK(cudaMemcpyAsync(s->clouds_raw, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            scale_clouds_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, stream>>>(s->clouds_raw, s->clouds, (uint32_t)n_pts, p.w2s_w, p.w2s_h, p.w2s_d);
+            CU_CHECK(cudaGetLastError());
+            if (launches) *launches += 1;
             for (int k = 0; k < 3; k++) {
                 float lo = INFINITY, hi = -INFINITY;
                 for (size_t i = 0; i < n_pts; i++) {
@@ -227,6 +233,8 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             s->clouds_src = cfg->light_clouds;
             s->clouds_k = cfg->n_light_clouds;
             s->clouds_m = p.M;
+            s->clouds_w = cfg->width;
+            s->clouds_h = cfg->height;
         }
         p.clouds = s->clouds;
         for (int k = 0; k < 3; k++) {
@@ -440,7 +448,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->clouds, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);

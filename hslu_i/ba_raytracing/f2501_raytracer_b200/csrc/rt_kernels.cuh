@@ -41,7 +41,7 @@ struct RenderParams {
     float eps_d;           // default_epsilon_distance component (vector.rs:697-700)
     float aa_off[2 * MAX_AA];
     float sample_scale;    // 1 / S
-    const float *clouds;   // K x M x 3
+    const float4 *clouds;  // K x M cloud points, already scaled to scene units: p * (w2s_w, w2s_h, w2s_d) (scale_clouds_kernel)
     float cloud_lo[3], cloud_hi[3];  // component-wise bounds of all cloud points (shadow beams)
     uint32_t K;
     unsigned long long seed;
@@ -100,26 +100,36 @@ RT_DEV void primary_ray(const RenderParams &p, uint32_t pix_x, uint32_t pix_y, u
 // calculate_lighting (raytracer_renderer.rs:773-870) with PointLight::to_point_light_cloud
 // (light.rs:183-225), the shadow query and PointLight::calculate_contribution_at (light.rs:261-299).
 // Returns the diffuse and specular terms this light copy adds (zero when occluded / facing away).
+// One light copy as the lighting loop sees it (PointLight::to_point_light_cloud, light.rs:183-225).
+struct LightCopy {
+    float3 pos, color;
+    float intensity;
+};
+// light `li` itself; with soft shadows the intensity is already the per-copy intensity / M (light.rs:194)
+RT_DEV LightCopy load_light(const RenderParams &p, uint32_t li) {
+    const float4 l0 = __ldg(p.sc.lights + 2 * li), l1 = __ldg(p.sc.lights + 2 * li + 1);
+    LightCopy L;
+    L.pos = f3(l0.x, l0.y, l0.z);
+    L.color = f3(l1.x, l1.y, l1.z);
+    L.intensity = p.M > 1 ? p.inv_M * l0.w : l0.w;
+    return L;
+}
+// copy `cpy` of cloud `cloud`: position + p * (w2s_w, w2s_h, w2s_d) (the product is precomputed per point)
+RT_DEV float3 copy_position(const RenderParams &p, float3 lpos, uint32_t cloud, uint32_t cpy) {
+    const float4 rp = __ldg(p.clouds + (size_t)cloud * p.M + cpy);
+    return lpos + f3(rp.x, rp.y, rp.z);
+}
+
 // `cand` / `n_cand` (>= 0): the beam's candidate list for this (shading point, light), see beam_collect;
 // n_cand < 0: the shadow query walks the BVH itself.
 // BEAM: the caller built a beam; its overflow fallback (n_cand < 0) is the out-of-line traversal.
 template <bool COUNT, bool BEAM = false>
-RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, uint32_t li, uint32_t cpy,
-                       uint32_t cloud, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
+RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, float3 lpos, float lint,
+                       float3 lcol, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
                        int32_t *last_occluder = nullptr) {
     const DScene &sc = p.sc;
     dc = splat(0.0f);
     spc = splat(0.0f);
-    const float4 l0 = __ldg(sc.lights + 2 * li), l1 = __ldg(sc.lights + 2 * li + 1);
-    float3 lpos = f3(l0.x, l0.y, l0.z);
-    float lint = l0.w;
-    const float3 lcol = f3(l1.x, l1.y, l1.z);
-    if (p.M > 1) {
-        const float *cp = p.clouds + ((size_t)cloud * p.M + cpy) * 3;
-        float3 rp = f3(__ldg(cp), __ldg(cp + 1), __ldg(cp + 2));
-        lpos = lpos + rp * f3(p.w2s_w, p.w2s_h, p.w2s_d);
-        lint = p.inv_M * lint;
-    }
     const float3 l2p = lpos - hp;
     const float3 ldir = normalized3(l2p);
     const float3 q = hp + ldir * p.eps_d;
@@ -341,7 +351,9 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
                                                                    : cloud_index(p.seed, packet_noaa ? __float_as_uint(r2.z) / 8u : __float_as_uint(r2.z),
                                                                                  __float_as_uint(r2.w), li, p.K))
                                             : 0u;
-                shade_pair<COUNT>(p, hp, hn, view, mcolor, mshininess, li, cpy, ci, cull, cn, dc, spc);
+                const LightCopy L = load_light(p, li);
+                shade_pair<COUNT>(p, hp, hn, view, mcolor, mshininess, p.M > 1 ? copy_position(p, L.pos, ci, cpy) : L.pos, L.intensity, L.color, cull,
+                                  cn, dc, spc);
             }
             if (n_live == 32) {
                 sum_d = sum_d + dc;  // pair (l, s = lane): this lane's own hit, next light in order
@@ -561,12 +573,13 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         uint32_t cand[BEAM_MAX_CAND];
         int n_cand = -1;
         int32_t last_occluder = -1;
+        LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
+        if (p.LM > 0) L = load_light(p, li0);
         if (BEAM) {
-            const float4 l0 = __ldg(sc.lights + 2 * li0);
-            const float3 lpos = f3(l0.x, l0.y, l0.z), w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
-            // the same float operations as shade_pair's `lpos + rp * w2s`, which are monotonic in rp
-            const float3 lmin = lpos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
-            const float3 lmax = lpos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
+            const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
+            // the same float operations as the copies' `lpos + rp * w2s`, which are monotonic in rp
+            const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
+            const float3 lmax = L.pos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
             const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
             const Beam beam = make_beam(P, lmin, lmax, pad);
             n_cand = beam_collect<COUNT>(sc, beam, cand, cn);
@@ -577,8 +590,9 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         }
         for (uint32_t l = 0; l < n_in_group; l++) {
             float3 dc, spc;
-            shade_pair<COUNT, BEAM>(p, P, N, d, m.color, m.shininess, p.M > 1 ? li0 : l, p.M > 1 ? l : 0u, cloud, cull, cn, dc, spc, cand, n_cand,
-                                    &last_occluder);
+            if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
+            const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
+            shade_pair<COUNT, BEAM>(p, P, N, d, m.color, m.shininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand, &last_occluder);
             sum_d = sum_d + dc;
             sum_s = sum_s + spc;
         }
@@ -604,6 +618,14 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         atomicAdd(p.counters + 4, cn.sph);
         atomicAdd(p.counters + 5, cn.beam_prim);
     }
+}
+
+// raw cloud points (K x M x [f32;3], as handed over) -> float4 table scaled to scene units, the
+// `p * (w2s_w, w2s_h, w2s_d)` of to_point_light_cloud (light.rs:208-216) evaluated once per point
+__global__ void scale_clouds_kernel(const float *__restrict__ raw, float4 *__restrict__ out, uint32_t n, float w2s_w, float w2s_h, float w2s_d) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(raw[3 * i] * w2s_w, raw[3 * i + 1] * w2s_h, raw[3 * i + 2] * w2s_d, 0.0f);
 }
 
 // antialiased_raytrace's reduction (raytracer_renderer.rs:974-1015) + to_output + ChunkView::set.
