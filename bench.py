@@ -45,6 +45,9 @@ WORKLOADS = {
 # canonical algorithmic costs
 F_BOX, F_TRI, F_SPH = 22, 45, 22
 B_BOX, B_TRI, B_SPH = 32, 52, 20
+# beam-vs-triangle culling test (rt_device.cuh beam_filter): 3 sub, 2 cross (18), w = g - wu - wv (6), 4 dot (20),
+# 4 abs-dot (20), margins (10); once per (shading point, light, candidate triangle), not per ray
+F_BEAM_TRI = 77
 
 
 class ClockSampler:
@@ -230,14 +233,30 @@ def main() -> None:
     # ---- untimed: work counters of this rank's tiles (counter build of the same kernels)
     import ctypes as C
 
-    rc_count = RenderConfig(L.Config(), rc.aa_table, rc.light_clouds)
-    C.memmove(C.byref(rc_count.cfg), C.byref(tiled.rc.cfg), C.sizeof(L.Config))
-    rc_count.cfg.flags |= L.FLAG_COUNT_WORK
-    st = dev.render_device(rc_count, tiled.slab.data_ptr(), tiled.mask.data_ptr(), None, want_stats=True)
-    counts = {k: allsum(float(st[k])) for k in ("closest_rays", "shadow_rays", "box_tests", "triangle_tests", "sphere_tests")}
+    def count_pass(extra_flags: int) -> dict:
+        rcc = RenderConfig(L.Config(), rc.aa_table, rc.light_clouds)
+        C.memmove(C.byref(rcc.cfg), C.byref(tiled.rc.cfg), C.sizeof(L.Config))
+        rcc.cfg.flags |= L.FLAG_COUNT_WORK | extra_flags
+        stc = dev.render_device(rcc, tiled.slab.data_ptr(), tiled.mask.data_ptr(), None, want_stats=True)
+        out = {k: allsum(float(stc[k])) for k in ("closest_rays", "shadow_rays", "box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests",
+                                                  "prepass_box_tests", "prepass_triangle_tests", "prepass_sphere_tests")}
+        out["kernel_launches"] = int(stc["kernel_launches"])
+        return out
+
+    counts = count_pass(0)                          # what the timed kernels execute (shadow beams)
+    counts_ray = count_pass(L.FLAG_PER_RAY_SHADOWS)  # the same frame with one BVH walk per shadow ray
+    st = counts
     rays_per_frame = counts["closest_rays"] + counts["shadow_rays"]
-    flops_alg = counts["box_tests"] * F_BOX + counts["triangle_tests"] * F_TRI + counts["sphere_tests"] * F_SPH
-    bytes_alg = counts["box_tests"] * B_BOX + counts["triangle_tests"] * B_TRI + counts["sphere_tests"] * B_SPH
+    assert rays_per_frame == counts_ray["closest_rays"] + counts_ray["shadow_rays"]
+
+    def alg(c):  # tests of the dominant kernel alone: totals minus the primary pre-pass kernel's share
+        nb, nt, ns = c["box_tests"] - c["prepass_box_tests"], c["triangle_tests"] - c["prepass_triangle_tests"], c["sphere_tests"] - c["prepass_sphere_tests"]
+        fl = nb * F_BOX + nt * F_TRI + ns * F_SPH + c["beam_triangle_tests"] * F_BEAM_TRI
+        by = nb * B_BOX + (nt + c["beam_triangle_tests"]) * B_TRI + ns * B_SPH
+        return fl, by
+
+    flops_alg, bytes_alg = alg(counts)
+    flops_ray, bytes_ray = alg(counts_ray)
 
     fp32_peak = C.c_double(0.0)
     L.check(lib.rt_measure_fp32_peak(local_rank, C.byref(fp32_peak)))
@@ -267,6 +286,8 @@ def main() -> None:
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if rank == 0 else None
+    dom_ms = dev.kernel_times(min(args.steps, 64))  # dominant kernel alone, one CUDA-event pair per timed step
+    dom_ms_max = allmax(float(dom_ms.mean()) if len(dom_ms) else 0.0)
     step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
     kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
     step_ms = allmax(step_ms)
@@ -311,7 +332,17 @@ def main() -> None:
         except (OSError, ValueError):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        kernel_ms = kern_ms_max / args.steps
+        kernel_ms = dom_ms_max                    # the dominant kernel's own launch duration (max over ranks of the per-rank mean)
+        render_ms = kern_ms_max / args.steps      # primary + dominant + resolve kernels
+        bounces = bool(rc.cfg.flags & (L.FLAG_REFLECTIONS | L.FLAG_REFRACTIONS))
+        dominant_kernel = "render_kernel<false>" if bounces else ("direct_kernel<false,true>" if rc.cfg.light_multiplicator > 1 else "direct_kernel<false,false>")
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
+            tj = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(args.workload)
+            if tj and tj.get("kernel") == dominant_kernel and world == 1:
+                traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except (OSError, ValueError):
+            pass
         ach_tflops = flops_alg / world / (kernel_ms * 1e-3) / 1e12  # per GPU, dominant kernel
         line = {
             "metric": "rays_per_second", "value": rays_per_frame / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": world,
@@ -326,14 +357,24 @@ def main() -> None:
             "ms_per_frame": ms_per_step,
             "e2e": {"value": rays_per_frame / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_frame": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(args.steps * (int(st["kernel_launches"]) + (0 if world == 1 else 2 * world))),
+            "gpu_launches": int(args.steps * (int(st["kernel_launches"]) + (0 if world == 1 else 1))),
+            "executed_tests_per_ray": {k: counts[k] / rays_per_frame for k in ("box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests")},
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
-                         "frac": ach_tflops / fp32_peak.value if fp32_peak.value else None, "traffic": None,
-                         "kernel": "render_kernel<false>", "kernel_ms": kernel_ms,
+                         "frac": ach_tflops / fp32_peak.value if fp32_peak.value else None, "traffic": traffic,
+                         "kernel": dominant_kernel, "kernel_ms": kernel_ms, "all_render_kernels_ms": render_ms,
                          "peak_source": "measured in this run: rt_measure_fp32_peak (register FFMA microbenchmark); MEASURED_PEAKS.json has no FP32 figure",
-                         "algorithmic": f"{F_BOX} flop/box test, {F_TRI} flop/triangle test, {F_SPH} flop/sphere test (SURVEY 8d); "
-                                        f"{int(counts['box_tests'])} box, {int(counts['triangle_tests'])} triangle, {int(counts['sphere_tests'])} sphere tests per frame",
+                         "algorithmic": f"EXECUTED tests x canonical flop (SURVEY 8d): {F_BOX}/box, {F_TRI}/triangle, {F_SPH}/sphere, {F_BEAM_TRI}/beam-triangle test; "
+                                        f"{int(counts['box_tests'])} box, {int(counts['triangle_tests'])} triangle, {int(counts['sphere_tests'])} sphere, "
+                                        f"{int(counts['beam_triangle_tests'])} beam-triangle tests per frame, of which the primary pre-pass kernel's "
+                                        f"{int(counts['prepass_box_tests'])} / {int(counts['prepass_triangle_tests'])} / {int(counts['prepass_sphere_tests'])} are left out",
+                         "per_ray_traversal_equivalent": {
+                             "achieved": flops_ray / world / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                             "frac": flops_ray / world / (kernel_ms * 1e-3) / 1e12 / fp32_peak.value if fp32_peak.value else None,
+                             "note": "the same frame's test counts when every shadow ray walks the BVH itself (RT_FLAG_PER_RAY_SHADOWS counter build: "
+                                     f"{int(counts_ray['box_tests'])} box, {int(counts_ray['triangle_tests'])} triangle, {int(counts_ray['sphere_tests'])} sphere) "
+                                     "over the measured kernel time: the work shadow beams avoid counts as done here, it does not in `achieved`"},
+                         "traffic_source": traffic_src,
                          "hbm": {"achieved": bytes_alg / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_alg / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": "algorithmic node/primitive bytes; the scene is L1/L2 resident, so this is cache not DRAM traffic"}},

@@ -68,6 +68,7 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
         ("box_tests", C.c_uint64), ("triangle_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("beam_triangle_tests", C.c_uint64),
+        ("prepass_box_tests", C.c_uint64), ("prepass_triangle_tests", C.c_uint64), ("prepass_sphere_tests", C.c_uint64),
     ]
 
     def as_dict(self) -> dict:
@@ -95,9 +96,11 @@ def _declare(lib: C.CDLL) -> None:
         "rt_scene_destroy": (None, [vp]),
         "rt_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),
         "rt_render_device": (i32, [vp, P(Config), vp, vp, vp, P(Stats)]),
+        "rt_kernel_times": (i32, [vp, u32, vp, P(u32)]),
         "rt_tile_local_rows": (u32, [P(Config)]),
         "rt_tile_row": (u32, [P(Config), u32]),
         "rt_scatter_tile_rows": (i32, [P(Config), vp, vp, u32, vp]),
+        "rt_place_tiles": (i32, [P(Config), vp, u64, vp, vp, vp]),
         "rt_trace_closest": (i32, [vp, u32, vp, u32, vp, vp]),
         "rt_trace_shadow": (i32, [vp, u32, vp, vp, u32, vp]),
         "rt_sampler_aa_table": (i32, [u64, u32, i32, vp, u32]),

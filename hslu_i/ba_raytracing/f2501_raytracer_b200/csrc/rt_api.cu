@@ -63,7 +63,17 @@ struct rt_scene {
     size_t pinned_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // ring of event pairs around the dominant kernel (direct_kernel / render_kernel) of the last renders
+    static constexpr uint32_t KERNEL_EVENT_RING = 64;
+    cudaEvent_t kev[KERNEL_EVENT_RING][2] = {};
+    uint64_t kev_count = 0;
 };
+
+static cudaEvent_t kernel_event(rt_scene *s, int which) {
+    cudaEvent_t &e = s->kev[s->kev_count % rt_scene::KERNEL_EVENT_RING][which];
+    if (!e && cudaEventCreate(&e) != cudaSuccess) e = nullptr;
+    return e;
+}
 
 static uint32_t local_rows_of(const rt_config *c) {
     if (c->tile_world <= 1 || c->tile_rows == 0) return c->height;
@@ -254,7 +264,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     if (p.local_rows == 0) return RT_OK;
     CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
     const bool count = (cfg->flags & RT_FLAG_COUNT_WORK) != 0;
-    if (count) CU_CHECK(cudaMemsetAsync(s->counters, 0, 8 * sizeof(unsigned long long), stream));
+    if (count) CU_CHECK(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), stream));
     int grid = s->sm_count * (count ? s->ctas_per_sm_count : s->ctas_per_sm);
     uint32_t warps_needed = (p.n_items + 31) / 32;
     grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, (warps_needed + CTA_WARPS - 1) / CTA_WARPS));
@@ -270,11 +280,14 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     if (launches) *launches += 1;
     if (bounces) {
         // per-sample reflection / refraction trees: persistent megakernel
+        if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
         if (count)
             render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
         else
             render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
         CU_CHECK(cudaGetLastError());
+        if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
+        s->kev_count++;
         if (launches) *launches += 1;
     } else {
         // direct lighting only: one pass per light group over all samples
@@ -305,8 +318,11 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
                            std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
         auto kernel = count ? (beams ? direct_kernel<true, true> : direct_kernel<true, false>) : (beams ? direct_kernel<false, true> : direct_kernel<false, false>);
+        if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
         kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
         CU_CHECK(cudaGetLastError());
+        if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
+        s->kev_count++;
         if (launches) *launches += 1;
     }
     uint32_t n_pix = p.local_rows * p.width;
@@ -317,7 +333,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
 }
 
 static int fetch_counters(rt_scene *s, rt_stats *st) {
-    unsigned long long c[8];
+    unsigned long long c[16];
     CU_CHECK(cudaMemcpy(c, s->counters, sizeof(c), cudaMemcpyDeviceToHost));
     st->closest_rays = c[0];
     st->shadow_rays = c[1];
@@ -325,6 +341,9 @@ static int fetch_counters(rt_scene *s, rt_stats *st) {
     st->triangle_tests = c[3];
     st->sphere_tests = c[4];
     st->beam_triangle_tests = c[5];
+    st->prepass_box_tests = c[8];
+    st->prepass_triangle_tests = c[9];
+    st->prepass_sphere_tests = c[10];
     return RT_OK;
 }
 
@@ -437,7 +456,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         s->ctas_per_sm_direct = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
         s->ctas_per_sm_direct_count = 1;
-    if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+    if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
         cudaEventCreate(&s->ev1) != cudaSuccess)
         return fail(rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -456,6 +475,9 @@ void rt_scene_destroy(rt_scene *s) {
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    for (auto &pair : s->kev)
+        for (cudaEvent_t e : pair)
+            if (e) cudaEventDestroy(e);
     delete s;
 }
 
@@ -551,6 +573,21 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
     return RT_OK;
 }
 
+int rt_kernel_times(rt_scene *s, uint32_t n, float *out_ms, uint32_t *out_n) {
+    if (!s || !out_ms || !out_n) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_kernel_times: null argument");
+    CU_CHECK(cudaSetDevice(s->device));
+    const uint64_t have = std::min<uint64_t>(s->kev_count, rt_scene::KERNEL_EVENT_RING);
+    const uint32_t m = (uint32_t)std::min<uint64_t>(n, have);
+    for (uint32_t i = 0; i < m; i++) {  // oldest first
+        const uint64_t idx = (s->kev_count - m + i) % rt_scene::KERNEL_EVENT_RING;
+        if (!s->kev[idx][0] || !s->kev[idx][1]) return rt_fail(RT_ERR_CUDA, "rt_kernel_times: events unavailable");
+        CU_CHECK(cudaEventSynchronize(s->kev[idx][1]));
+        CU_CHECK(cudaEventElapsedTime(&out_ms[i], s->kev[idx][0], s->kev[idx][1]));
+    }
+    *out_n = m;
+    return RT_OK;
+}
+
 int rt_scatter_tile_rows(const rt_config *cfg, const void *d_slab, void *d_frame, uint32_t elem_size, void *cuda_stream) {
     if (!cfg || !d_slab || !d_frame || (elem_size != 1 && elem_size != 4))
         return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scatter_tile_rows: bad argument");
@@ -560,6 +597,17 @@ int rt_scatter_tile_rows(const rt_config *cfg, const void *d_slab, void *d_frame
     size_t total = (size_t)row_bytes * rows;
     scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
         (const uint8_t *)d_slab, (uint8_t *)d_frame, row_bytes, rows, cfg->tile_rows, cfg->tile_rank, cfg->tile_world);
+    CU_CHECK(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_place_tiles(const rt_config *cfg, const void *d_slabs, uint64_t slab_stride_pixels, void *d_frame, void *d_hit_mask, void *cuda_stream) {
+    if (!cfg || !d_slabs || !d_frame || cfg->tile_world == 0 || cfg->tile_rows == 0 || cfg->width == 0 || cfg->height == 0)
+        return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_place_tiles: bad argument");
+    const size_t total = (size_t)cfg->width * cfg->height;
+    place_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(
+        (const uint32_t *)d_slabs, (size_t)slab_stride_pixels, (uint32_t *)d_frame, (uint8_t *)d_hit_mask, cfg->width, cfg->height, cfg->tile_rows,
+        cfg->tile_world);
     CU_CHECK(cudaGetLastError());
     return RT_OK;
 }

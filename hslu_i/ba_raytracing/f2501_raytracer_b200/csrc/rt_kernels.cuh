@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(128) primary_kernel(const RenderParams p) {
         atomicAdd(p.counters + 2, cn.box);
         atomicAdd(p.counters + 3, cn.tri);
         atomicAdd(p.counters + 4, cn.sph);
+        atomicAdd(p.counters + 8, cn.box);  // ... and once more as the pre-pass's own share
+        atomicAdd(p.counters + 9, cn.tri);
+        atomicAdd(p.counters + 10, cn.sph);
     }
 }
 
@@ -708,6 +711,21 @@ __global__ void scatter_rows_kernel(const uint8_t *__restrict__ slab, uint8_t *_
         row = (t * tile_world + tile_rank) * tile_rows + r;
     }
     frame[(size_t)row * row_bytes + off] = slab[i];
+}
+
+// after the NCCL gather, all ranks at once: frame pixel (row, x) comes from rank (row / tile_rows) % world,
+// local row (row / tile_rows / world) * tile_rows + row % tile_rows of that rank's slab (slabs are `slab_stride`
+// u32 apart).  A hit pixel is 0xFFrrggbb and a miss is 0 (resolve_kernel), so the hit mask is slab != 0.
+__global__ void place_tiles_kernel(const uint32_t *__restrict__ slabs, size_t slab_stride, uint32_t *__restrict__ frame, uint8_t *__restrict__ mask,
+                                   uint32_t width, uint32_t height, uint32_t tile_rows, uint32_t tile_world) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)width * height) return;
+    const uint32_t row = (uint32_t)(i / width), x = (uint32_t)(i - (size_t)row * width);
+    const uint32_t t = row / tile_rows, r = row - t * tile_rows;
+    const uint32_t rank = t % tile_world, lr = (t / tile_world) * tile_rows + r;
+    const uint32_t v = slabs[rank * slab_stride + (size_t)lr * width + x];
+    frame[i] = v;
+    if (mask) mask[i] = v != 0u;
 }
 
 }  // namespace rtd

@@ -6,7 +6,7 @@ exchange.  Here image rows are dealt out in tiles of `tile_rows` rows, tile t ->
 (interleaved because cost is very non-uniform: glass spheres vs. the black border).  Every rank
 renders its tiles into a compact device slab (rt_render_device); the only collective is the gather
 of the finished slabs to rank 0 over NVLink (torch.distributed / NCCL), after which rank 0 places
-the rows with rt_scatter_tile_rows.  Per-pixel sampler streams are keyed by (seed, x, y, light), so
+all rows with rt_place_tiles (one kernel; the hit mask is `pixel != 0`).  Per-pixel sampler streams are keyed by (seed, x, y, light), so
 the image does not depend on the world size.
 """
 from __future__ import annotations
@@ -40,13 +40,13 @@ class TiledRenderer:
         dev = torch.device("cuda", scene.device)
         self.slab = torch.zeros(self.pad_rows * self.width, dtype=torch.int32, device=dev)
         self.mask = torch.zeros(self.pad_rows * self.width, dtype=torch.uint8, device=dev)
-        self.frame = self.frame_mask = self.gathered = self.gathered_mask = None
+        self.frame = self.frame_mask = self.gathered = None
         if rank == 0:
             self.frame = torch.zeros(self.height * self.width, dtype=torch.int32, device=dev)
             self.frame_mask = torch.zeros(self.height * self.width, dtype=torch.uint8, device=dev)
-            if world > 1:
-                self.gathered = [torch.zeros_like(self.slab) for _ in range(world)]
-                self.gathered_mask = [torch.zeros_like(self.mask) for _ in range(world)]
+            if world > 1:  # one contiguous buffer: slab r at r * pad_rows * width
+                self.gathered = torch.zeros(world * self.pad_rows * self.width, dtype=torch.int32, device=dev)
+                self.gather_list = list(self.gathered.view(world, -1).unbind(0))
 
     def render_local(self) -> None:
         """Enqueue this rank's tiles on torch's current stream (no host sync)."""
@@ -54,7 +54,8 @@ class TiledRenderer:
         self.scene.render_device(self.rc, self.slab.data_ptr(), self.mask.data_ptr(), stream)
 
     def gather(self, with_mask: bool = True) -> None:
-        """Gather the slabs on rank 0 and place their rows into the full frame."""
+        """Gather the slabs on rank 0 (ONE collective: a slab pixel is 0xFFrrggbb for a hit and 0 for a
+        miss, so the hit mask travels inside it) and place all rows into the full frame (one kernel)."""
         torch = self.torch
         lib = L.load()
         stream = torch.cuda.current_stream().cuda_stream
@@ -65,15 +66,11 @@ class TiledRenderer:
             return
         import torch.distributed as dist
 
-        dist.gather(self.slab, self.gathered if self.rank == 0 else None, dst=0)
-        if with_mask:
-            dist.gather(self.mask, self.gathered_mask if self.rank == 0 else None, dst=0)
+        dist.gather(self.slab, self.gather_list if self.rank == 0 else None, dst=0)
         if self.rank == 0:
-            for r in range(self.world):
-                cfg_r = self.rc_full.with_tiles(self.tile_rows, r, self.world).cfg
-                L.check(lib.rt_scatter_tile_rows(C.byref(cfg_r), self.gathered[r].data_ptr(), self.frame.data_ptr(), 4, stream))
-                if with_mask:
-                    L.check(lib.rt_scatter_tile_rows(C.byref(cfg_r), self.gathered_mask[r].data_ptr(), self.frame_mask.data_ptr(), 1, stream))
+            cfg = self.rc_full.with_tiles(self.tile_rows, 0, self.world).cfg
+            L.check(lib.rt_place_tiles(C.byref(cfg), self.gathered.data_ptr(), self.pad_rows * self.width, self.frame.data_ptr(),
+                                       self.frame_mask.data_ptr() if with_mask else None, stream))
 
     def step(self) -> None:
         self.render_local()

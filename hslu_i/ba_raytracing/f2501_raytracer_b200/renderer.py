@@ -131,6 +131,13 @@ class DeviceScene:
         L.check(self._lib.rt_render_device(self._h, C.byref(rc.cfg), d_argb, d_mask, stream, C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
+    def kernel_times(self, n: int = 64) -> np.ndarray:
+        """rt_kernel_times: device ms of the dominant kernel of the last (up to 64) render calls."""
+        out = np.zeros(max(n, 1), np.float32)
+        got = C.c_uint32(0)
+        L.check(self._lib.rt_kernel_times(self._h, n, L.ptr(out), C.byref(got)))
+        return out[: got.value]
+
     def trace_closest(self, rays: np.ndarray, flags: int = 0) -> tuple[np.ndarray, np.ndarray]:
         rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 6)
         t = np.zeros(len(rays), np.float32)

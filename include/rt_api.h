@@ -145,6 +145,9 @@ typedef struct rt_stats {
     uint64_t sphere_tests;
     uint64_t kernel_launches; /* kernels launched by this call */
     uint64_t beam_triangle_tests; /* shadow-beam vs triangle culling tests (one per beam, not per ray) */
+    uint64_t prepass_box_tests;      /* share of box/triangle/sphere_tests done by the primary-ray pre-pass */
+    uint64_t prepass_triangle_tests; /* kernel (they are included in the totals above) */
+    uint64_t prepass_sphere_tests;
 } rt_stats;
 
 typedef struct rt_scene rt_scene; /* opaque: device-resident SoA geometry + BVH */
@@ -182,6 +185,11 @@ int rt_render(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t
 int rt_render_device(rt_scene *scene, const rt_config *cfg, void *d_out_argb, void *d_out_hit_mask,
                      void *cuda_stream, rt_stats *stats);
 
+/* Device durations (ms, CUDA events on the launching stream) of the DOMINANT kernel -- direct_kernel
+ * (no bounces) or render_kernel -- of the last min(n, 64) render calls on this scene, oldest first;
+ * *out_n receives how many were written.  Synchronises on the newest one.  Measurement only. */
+int rt_kernel_times(rt_scene *scene, uint32_t n, float *out_ms, uint32_t *out_n);
+
 /* Row-tile bookkeeping shared by every rank. */
 uint32_t rt_tile_local_rows(const rt_config *cfg);              /* rows this rank renders */
 uint32_t rt_tile_row(const rt_config *cfg, uint32_t local_row); /* image row of a local row */
@@ -190,6 +198,12 @@ uint32_t rt_tile_row(const rt_config *cfg, uint32_t local_row); /* image row of 
  * NCCL gather.  `d_slab` holds rt_tile_local_rows rows of width u32 (or u8 when elem_size==1). */
 int rt_scatter_tile_rows(const rt_config *cfg_of_rank, const void *d_slab, void *d_frame,
                          uint32_t elem_size, void *cuda_stream);
+
+/* The same for ALL ranks in one launch: `d_slabs` holds the tile_world gathered slabs, slab r starting
+ * at pixel r * slab_stride_pixels; writes the full frame and (optional) the hit mask, which is
+ * `pixel != 0` (hit pixels carry alpha 0xFF, miss pixels of a slab are 0). */
+int rt_place_tiles(const rt_config *cfg, const void *d_slabs, uint64_t slab_stride_pixels, void *d_frame,
+                   void *d_hit_mask, void *cuda_stream);
 
 /* Debug/parity entry points: raw queries against the device BVH for arbitrary rays
  * (host arrays).  rays: n x 6 floats (origin, un-normalised direction).
