@@ -45,6 +45,12 @@ struct rt_scene {
     DirectState *direct_state = nullptr;  // running light sums between the passes of direct_kernel
     size_t direct_cap = 0;
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
+    HelpQueue *help_queue = nullptr;        // publication queue of very expensive units (direct_kernel)
+    RenderParams *d_params = nullptr;       // global-memory copy of the kernel parameters for direct_kernel's out-of-line paths
+    RenderParams *h_params = nullptr;       // pinned staging buffers of it (ring: a copy must outlive its async upload)
+    uint32_t h_params_next = 0;
+    float4 *help_scratch = nullptr;         // per owner warp: M copies x 32 samples x 2 float4
+    size_t help_scratch_cap = 0;
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
     float *clouds_raw = nullptr;  // K x M x 3 cloud points, as handed over
@@ -317,9 +323,36 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         // shadow beams need M copies per light and usable bounds of the cloud points
         const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
                            std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
-        auto kernel = count ? (beams ? direct_kernel<true, true> : direct_kernel<true, false>) : (beams ? direct_kernel<false, true> : direct_kernel<false, false>);
+        // few units per warp (a rank's share of a multi-GPU frame): the tail of the launch matters more than the
+        // last 6 % of steady-state throughput -> the variant that shares very expensive units between warps
+        const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / ((uint64_t)dgrid * CTA_WARPS));
+        uint32_t share_below = 100;
+        if (const char *e = getenv("RT_SHARE_BELOW")) share_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
+        const bool share = beams && pd.M <= 32 && (size_t)dgrid * CTA_WARPS <= HELP_MAX_WARPS && units_per_warp < share_below;
+        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HelpQueue *, float4 *, const RenderParams *);
+        kernel_t kernel;
+        if (count)
+            kernel = beams ? (share ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
+        else
+            kernel = beams ? (share ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
+        HelpQueue *hq = nullptr;
+        if (share) {
+            if (!s->help_queue) CU_CHECK(cudaMalloc((void **)&s->help_queue, sizeof(HelpQueue)));
+            rc = grow(s->help_scratch, s->help_scratch_cap, (size_t)dgrid * CTA_WARPS * pd.M * 32 * 2 * sizeof(float4));
+            if (rc) return rc;
+            CU_CHECK(cudaMemsetAsync(s->help_queue, 0, sizeof(HelpQueue), stream));
+            hq = s->help_queue;
+        }
+        if (hq) {
+            constexpr uint32_t RING = 16;
+            if (!s->d_params) CU_CHECK(cudaMalloc((void **)&s->d_params, sizeof(RenderParams)));
+            if (!s->h_params) CU_CHECK(cudaMallocHost((void **)&s->h_params, RING * sizeof(RenderParams)));
+            RenderParams *stage = s->h_params + (s->h_params_next++ % RING);
+            *stage = pd;
+            CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
+        }
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state);
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state, hq, s->help_scratch, s->d_params);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
@@ -404,6 +437,13 @@ int rt_dbg_counters(unsigned long long *out8) {
 }
 #endif
 
+#ifdef RT_DBG_TAIL
+int rt_dbg_tail(unsigned long long *out, unsigned n_warps) {
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, rtd::g_dbg_tail, sizeof(unsigned long long) * 12 * n_warps);
+}
+#endif
+
 int rt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -452,9 +492,9 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
         s->ctas_per_sm_count = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
         s->ctas_per_sm_direct = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
         s->ctas_per_sm_direct_count = 1;
     if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
@@ -467,9 +507,10 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->help_queue, s->help_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (s->h_params) cudaFreeHost(s->h_params);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
     if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
     if (s->stream) cudaStreamDestroy(s->stream);

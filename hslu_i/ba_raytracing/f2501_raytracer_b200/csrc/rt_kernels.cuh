@@ -122,8 +122,9 @@ RT_DEV float3 copy_position(const RenderParams &p, float3 lpos, uint32_t cloud, 
 
 // `cand` / `n_cand` (>= 0): the beam's candidate list for this (shading point, light), see beam_collect;
 // n_cand < 0: the shadow query walks the BVH itself.
-// BEAM: the caller built a beam; its overflow fallback (n_cand < 0) is the out-of-line traversal.
-template <bool COUNT, bool BEAM = false>
+// MODE 0: the shadow query walks the BVH itself (inlined).  MODE 1: the caller built a beam; its overflow
+// fallback (n_cand < 0) is the out-of-line traversal.  MODE 2: out-of-line traversal only.
+template <bool COUNT, int MODE = 0>
 RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, float3 lpos, float lint,
                        float3 lcol, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
                        int32_t *last_occluder = nullptr) {
@@ -135,9 +136,11 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const float3 q = hp + ldir * p.eps_d;
     const float maxd = mag3(lpos - q);
     ShadowResult sh;
-    if (BEAM)
+    if (MODE == 1)
         sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, normalized3(ldir), maxd, cull, cn)
                          : trace_shadow_outlined<COUNT>(sc, q, normalized3(ldir), maxd, cull, &cn);
+    else if (MODE == 2)
+        sh = trace_shadow_outlined<COUNT>(sc, q, normalized3(ldir), maxd, cull, &cn);
     else
         sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
     // Everything below only matters when the light is unoccluded AND the surface faces it
@@ -510,9 +513,241 @@ RT_DEV void st_relaxed_gpu(float4 *ptr, float4 v) {
     asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <bool COUNT, bool BEAM>
-__global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
-                                                                                    unsigned int *counter, DirectState *state) {
+#ifdef RT_DBG_TAIL  // tuning experiments only: per-warp timeline of direct_kernel (rt_dbg_tail in rt_api.cu)
+__device__ unsigned long long g_dbg_tail[12 * 8192];
+RT_DEV unsigned long long dbg_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
+// ---- sharing of very expensive units ------------------------------------------------------------
+// A few units cost 20-30x the average: all 32 samples sit where the M shadow rays of one light run
+// lengthwise through dense geometry, their beams overflow and every ray walks the BVH itself.  One
+// such unit handed out late is the whole tail of the frame (and the chain keeps its successors
+// waiting).  Its owner therefore publishes it: the M copies become M independent sub-tasks (copy c
+// for all 32 samples) that warps pick up once the unit queue has run dry (the tail of the frame is
+// where it matters; polling between units would cost more than it gains).  Contributions go to a
+// scratch slab and the owner adds them up in copy order, so the result is bit-identical.
+constexpr uint32_t HELP_SLOTS = 64;        // publications open at the same time (more: the owner works alone)
+constexpr uint32_t HELP_MAX_WARPS = 8192;
+constexpr uint32_t HELP_CLOSED = 0x80000000u;
+struct HelpDesc {
+    unsigned int unit, next_copy, done, pad;
+};
+struct HelpQueue {
+    unsigned int units_done, pad0, pad1, pad2;
+    unsigned int open[HELP_SLOTS];  // owner warp + 1 of an open publication, 0 = free
+    HelpDesc desc[HELP_MAX_WARPS];  // per owner warp
+};
+RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
+
+// one sample of a batch, rebuilt from the primary pre-pass record (cheap next to its shadow rays)
+struct SampleRec {
+    bool valid, hit, transmissive;
+    float3 P, N, d, mcolor;
+    float mshininess, t;
+    uint32_t sample_index, pix_x, pix_y;
+};
+RT_DEV SampleRec rebuild_sample(const RenderParams &p, uint32_t item) {
+    const DScene &sc = p.sc;
+    SampleRec r;
+    const ItemInfo it = decode_item(p, item);
+    uint4 ph = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
+    if (it.valid) ph = p.primary_hits[item];
+    r.valid = it.valid;
+    r.hit = it.valid && (int32_t)ph.y >= 0;
+    r.sample_index = (it.ly * p.width + it.x) * p.S + it.s;
+    r.pix_x = it.x;
+    r.pix_y = tile_image_row(p, it.ly);
+    r.P = r.N = r.d = r.mcolor = splat(0.0f);
+    r.mshininess = r.t = 0.0f;
+    r.transmissive = false;
+    if (r.hit) {
+        float3 o, dir;
+        primary_ray(p, r.pix_x, r.pix_y, it.s, o, dir);
+        r.d = normalized3(dir);
+        r.t = __uint_as_float(ph.x);
+        const int32_t slot = (int32_t)ph.y;
+        const uint32_t meta = ph.w;
+        r.P = ray_at(o, r.d, r.t);
+        if (meta & rtb::PRIM_SPHERE) {
+            const float4 q0 = __ldg(sc.prims + 4 * (size_t)slot);
+            r.N = normalized3(r.P - f3(q0.x, q0.y, q0.z));
+        } else {
+            const float4 sn = __ldg(sc.shade_n + slot);
+            r.N = f3(sn.x, sn.y, sn.z);
+        }
+        const Material m = load_material(sc, meta & rtb::PRIM_MATERIAL_MASK);
+        r.mcolor = m.color;
+        r.mshininess = m.shininess;
+        r.transmissive = m.transmissive;
+    }
+    return r;
+}
+
+// The tail of direct_kernel: take copies of published units until every unit of the frame is finished.
+// Out of line (and reading the parameters from their global-memory copy) so that this rare path does not
+// weigh on the register allocation of the kernel's main loop.
+template <bool COUNT>
+__device__ __noinline__ uint32_t help_until_done(const RenderParams *gp, HelpQueue *hq, float4 *hscratch, uint32_t n_units, uint32_t n_batches,
+                                                 Counters *cn_out) {
+    const RenderParams &p = *gp;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
+    Counters cn = {0, 0, 0, 0, 0, 0};
+    uint32_t helped = 0;
+    for (;;) {
+        // (read first: once every unit is finished there is nothing left to help with)
+        const unsigned int finished = ld_volatile_u32(&hq->units_done);
+        if (finished >= n_units) break;
+        // every lane looks at two slots; owners of open publications are tried one after the other
+        const unsigned int e0 = ld_volatile_u32(&hq->open[lane]), e1 = ld_volatile_u32(&hq->open[lane + 32u]);
+        // (only publications that still have copies to hand out: no atomics on the exhausted ones)
+        const bool a0 = e0 != 0u && ld_volatile_u32(&hq->desc[e0 - 1u].next_copy) < p.M;
+        const bool a1 = e1 != 0u && ld_volatile_u32(&hq->desc[e1 - 1u].next_copy) < p.M;
+        unsigned m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1);
+        uint32_t h_unit = 0, h_copy = 0xFFFFFFFFu, h_owner = 0;
+        while ((m0 | m1) && h_copy == 0xFFFFFFFFu) {
+            const bool second = m0 == 0u;
+            const int src = __ffs(second ? m1 : m0) - 1;
+            if (second) m1 &= m1 - 1u; else m0 &= m0 - 1u;
+            const unsigned int e = __shfl_sync(FULL, second ? e1 : e0, src);
+            if (lane == 0) {
+                HelpDesc *ds = &hq->desc[e - 1u];
+                const unsigned int c = atomicAdd(&ds->next_copy, 1u);
+                if (c < p.M) {
+                    __threadfence();
+                    h_unit = ld_volatile_u32(&ds->unit);
+                    h_copy = c;
+                    h_owner = e - 1u;
+                }
+            }
+            h_copy = __shfl_sync(FULL, h_copy, 0);
+        }
+        if (h_copy == 0xFFFFFFFFu) {  // nothing to take right now: wait for the running units
+            __nanosleep(2000);
+            continue;
+        }
+        h_unit = __shfl_sync(FULL, h_unit, 0);
+        h_owner = __shfl_sync(FULL, h_owner, 0);
+        const uint32_t hg = h_unit / n_batches, hb = h_unit - hg * n_batches;
+        const SampleRec r = rebuild_sample(p, hb * 32u + lane);
+        if (r.hit) {
+            const LightCopy L = load_light(p, hg);
+            const uint32_t cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, hg, p.K);
+            float3 dc, spc;
+            shade_pair<COUNT, 2>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, copy_position(p, L.pos, cloud, h_copy), L.intensity, L.color, cull, cn, dc,
+                                 spc);
+            float4 *o = hscratch + (((size_t)h_owner * p.M + h_copy) * 32u + lane) * 2u;
+            st_relaxed_gpu(o, make_float4(dc.x, dc.y, dc.z, 0.0f));
+            st_relaxed_gpu(o + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&hq->desc[h_owner].done, 1u);
+        helped++;
+    }
+    if (COUNT && cn_out) {
+        cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
+        cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
+    }
+    return helped;
+}
+
+struct LightSums {  // running diffuse / specular light sums of one sample
+    float3 d, s;
+};
+// The owner's side of a published unit (see above): hands out the M copies of its light one by one to
+// itself and to whoever helps, then adds the contributions up in copy order.  Out of line for the same
+// reason as help_until_done.
+template <bool COUNT>
+__device__ __noinline__ LightSums run_published_unit(const RenderParams *gp, HelpQueue *hq, float4 *hscratch, uint32_t unit, uint32_t warp_id, bool hit,
+                                                     float3 P, float3 N, float3 d, float3 mcolor, float mshininess, float3 lpos0, float lint, float3 lcol,
+                                                     uint32_t cloud, const uint32_t *cand, int n_cand, LightSums sums, Counters *cn_out) {
+    const RenderParams &p = *gp;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    Counters cn = {0, 0, 0, 0, 0, 0};
+    int32_t last_occluder = -1;
+    float3 sd = sums.d, ss = sums.s;
+    HelpDesc *ds = &hq->desc[warp_id];
+    int my_slot = -1;
+    if (lane == 0) {
+        atomicExch(&ds->next_copy, HELP_CLOSED);  // stale helpers of the previous publication see "nothing left"
+        __threadfence();
+        *(volatile unsigned int *)&ds->unit = unit;
+        *(volatile unsigned int *)&ds->done = 0u;
+        __threadfence();
+        atomicExch(&ds->next_copy, 0u);  // open
+        __threadfence();
+    }
+    __syncwarp();
+    for (;;) {  // the owner works on its own publication like any helper (but keeps its beam lists)
+        uint32_t c = 0;
+        if (lane == 0) {
+            // make the publication visible in a free slot of the table (tried again before every copy:
+            // the table may be full in the middle of the frame, it never is at its tail)
+            for (uint32_t k = 0; k < 4u && my_slot < 0; k++) {
+                const uint32_t idx = (warp_id * 7u + k * 13u + ld_volatile_u32(&ds->next_copy)) % HELP_SLOTS;
+                if (ld_volatile_u32(&hq->open[idx]) == 0u && atomicCAS(&hq->open[idx], 0u, warp_id + 1u) == 0u) my_slot = (int)idx;
+            }
+            c = atomicAdd(&ds->next_copy, 1u);
+        }
+        c = __shfl_sync(FULL, c, 0);
+        if (c >= p.M) break;
+        if (hit) {
+            float3 dc, spc;
+            shade_pair<COUNT, 1>(p, P, N, d, mcolor, mshininess, copy_position(p, lpos0, cloud, c), lint, lcol, cull, cn, dc, spc,
+                                 cand, n_cand, &last_occluder);
+            float4 *o = hscratch + (((size_t)warp_id * p.M + c) * 32u + lane) * 2u;
+            st_relaxed_gpu(o, make_float4(dc.x, dc.y, dc.z, 0.0f));
+            st_relaxed_gpu(o + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&ds->done, 1u);
+    }
+    if (lane == 0) {
+        while (ld_volatile_u32(&ds->done) < p.M) {
+        }
+        if (my_slot >= 0) atomicExch(&hq->open[my_slot], 0u);
+    }
+    __syncwarp();
+    __threadfence();
+    if (hit) {
+        for (uint32_t c = 0; c < p.M; c++) {  // copy order = the reference's light order
+            const float4 *o = hscratch + (((size_t)warp_id * p.M + c) * 32u + lane) * 2u;
+            const float4 a = ld_relaxed_gpu(o), b2 = ld_relaxed_gpu(o + 1);
+            sd = sd + f3(a.x, a.y, a.z);
+            ss = ss + f3(b2.x, b2.y, b2.z);
+        }
+    }
+    if (COUNT && cn_out) {
+        cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
+        cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
+    }
+    sums.d = sd;
+    sums.s = ss;
+    return sums;
+}
+
+#ifndef RT_SHARE_MODE
+#define RT_SHARE_MODE 2  // 0: units are never shared, 1: when most samples of the batch overflowed, 2: when any did
+#endif
+#ifndef RT_DIRECT_MIN_CTAS
+#define RT_DIRECT_MIN_CTAS RT_MIN_CTAS_PER_SM
+#endif
+// SHARE: with the publication machinery (costs ~6 % of steady-state throughput, cuts the tail of the frame
+// from ~0.5 ms to ~0.1 ms): chosen by the host when a launch has few units per warp (multi-GPU tiles).
+template <bool COUNT, bool BEAM, bool SHARE>
+__global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
+                                                                                    unsigned int *counter, DirectState *state, HelpQueue *hq,
+                                                                                    float4 *hscratch, const RenderParams *gp) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const DScene &sc = p.sc;
@@ -520,98 +755,155 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool sharing = SHARE && BEAM && hq != nullptr && p.M <= 32u && warp_id < HELP_MAX_WARPS;
     Counters cn = {0, 0, 0, 0, 0, 0};
+#ifdef RT_DBG_TAIL
+    unsigned long long dbg_t0 = dbg_globaltimer(), dbg_spin = 0, dbg_last_start = 0, dbg_worst = 0, dbg_worst_info = 0, dbg_cur_info = 0;
+    unsigned long long dbg_ph0 = 0, dbg_ph1 = 0, dbg_ph2 = 0, dbg_help_time = 0;
+    uint32_t dbg_units = 0, dbg_helped = 0;
+#endif
     for (;;) {
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
         unit = __shfl_sync(FULL, unit, 0);
         if (unit >= n_units) break;
+#ifdef RT_DBG_TAIL
+        dbg_units++;
+        dbg_last_start = dbg_globaltimer();
+        dbg_cur_info = (unsigned long long)unit << 32;
+#endif
         const uint32_t group_index = unit / n_batches, batch = unit - group_index * n_batches;
         const bool last = group_index + 1 == n_groups;
         const uint32_t item = batch * 32u + lane;
-        const ItemInfo it = decode_item(p, item);
-        uint4 ph = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
-        if (it.valid) ph = p.primary_hits[item];
-        const bool hit = it.valid && (int32_t)ph.y >= 0;
-        const uint32_t sample_index = (it.ly * p.width + it.x) * p.S + it.s;
-        if (COUNT && it.valid && group_index == 0) cn.closest++;
-        if (!hit) {
-            if (it.valid && last) p.samples[sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            continue;  // lanes of a batch that missed simply sit this batch out
-        }
-        // rebuild the hit record of this lane's sample (cheap next to its shadow rays)
-        const uint32_t pix_x = it.x, pix_y = tile_image_row(p, it.ly);
-        float3 o, dir;
-        primary_ray(p, pix_x, pix_y, it.s, o, dir);
-        const float3 d = normalized3(dir);
-        const float t = __uint_as_float(ph.x);
-        const int32_t slot = (int32_t)ph.y;
-        const uint32_t meta = ph.w;
-        const float3 P = ray_at(o, d, t);
-        float3 N;
-        if (meta & rtb::PRIM_SPHERE) {
-            const float4 q0 = __ldg(sc.prims + 4 * (size_t)slot);
-            N = normalized3(P - f3(q0.x, q0.y, q0.z));
-        } else {
-            const float4 sn = __ldg(sc.shade_n + slot);
-            N = f3(sn.x, sn.y, sn.z);
-        }
-        const Material m = load_material(sc, meta & rtb::PRIM_MATERIAL_MASK);
+        const SampleRec r = rebuild_sample(p, item);
+        if (COUNT && r.valid && group_index == 0) cn.closest++;
+        // lanes of a batch that missed sit the batch out but stay with the warp
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
-        if (group_index > 0) {
-            // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
-            const uint32_t want = frame_tag + group_index - 1u;
-            float4 sd, ss;
-            do {
-                sd = ld_relaxed_gpu(&state[item].d);
-                ss = ld_relaxed_gpu(&state[item].s);
-            } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
-            sum_d = f3(sd.x, sd.y, sd.z);
-            sum_s = f3(ss.x, ss.y, ss.z);
-        }
         const uint32_t li0 = p.M > 1 ? group_index : 0u;
-        const uint32_t cloud = p.M > 1 ? cloud_index(p.seed, packet_noaa ? pix_x / 8u : pix_x, pix_y, li0, p.K) : 0u;
         const uint32_t n_in_group = p.M > 1 ? p.M : p.LM;
-        // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
-        uint32_t cand[BEAM_MAX_CAND];
+        uint32_t cloud = 0u;
+        uint32_t cand[BEAM_MAX_CAND];  // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
         int n_cand = -1;
         int32_t last_occluder = -1;
         LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
         if (p.LM > 0) L = load_light(p, li0);
-        if (BEAM) {
-            const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
-            // the same float operations as the copies' `lpos + rp * w2s`, which are monotonic in rp
-            const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
-            const float3 lmax = L.pos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
-            const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
-            const Beam beam = make_beam(P, lmin, lmax, pad);
-            n_cand = beam_collect<COUNT>(sc, beam, cand, cn);
-            if (n_cand > 0) {
+        if (r.hit) {
+            if (group_index > 0) {
+                // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
+                const uint32_t want = frame_tag + group_index - 1u;
+                float4 sd, ss;
+#ifdef RT_DBG_TAIL
+                const unsigned long long dbg_s0 = dbg_globaltimer();
+#endif
+                do {
+                    sd = ld_relaxed_gpu(&state[item].d);
+                    ss = ld_relaxed_gpu(&state[item].s);
+                } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
+#ifdef RT_DBG_TAIL
+                dbg_spin += dbg_globaltimer() - dbg_s0;
+#endif
+                sum_d = f3(sd.x, sd.y, sd.z);
+                sum_s = f3(ss.x, ss.y, ss.z);
+            }
+            if (p.M > 1) cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, li0, p.K);
+            if (BEAM) {
+                const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
+                // the same float operations as the copies' `lpos + rp * w2s`, which are monotonic in rp
+                const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
+                const float3 lmax = L.pos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
+                const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
+                const Beam beam = make_beam(r.P, lmin, lmax, pad);
                 const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
-                n_cand = beam_filter<COUNT>(sc, P, C - P, hh, cand, n_cand, cn);
+                n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn);
             }
         }
-        for (uint32_t l = 0; l < n_in_group; l++) {
-            float3 dc, spc;
-            if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
-            const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
-            shade_pair<COUNT, BEAM>(p, P, N, d, m.color, m.shininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand, &last_occluder);
-            sum_d = sum_d + dc;
-            sum_s = sum_s + spc;
+#ifdef RT_DBG_TAIL
+        const unsigned long long dbg_tb = dbg_globaltimer();
+#endif
+        bool share = false;
+        if (SHARE && BEAM && sharing) {
+            // some sample's beam overflowed: its M rays walk the BVH one by one and the whole warp waits for
+            // them (SIMT), so the unit costs the same whoever traces the other lanes -- publish the copies
+            __syncwarp();
+#if RT_SHARE_MODE == 1
+            share = 2 * __popc(__ballot_sync(FULL, r.hit && n_cand < 0)) > __popc(__ballot_sync(FULL, r.hit));
+#else
+            share = __ballot_sync(FULL, r.hit && n_cand < 0) != 0u;
+#endif
         }
-        if (!last) {
-            const float tag = __uint_as_float(frame_tag + group_index);
-            st_relaxed_gpu(&state[item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
-            st_relaxed_gpu(&state[item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
-        } else {
-            // single_raytrace without bounces (raytracer_renderer.rs:195-257)
-            const float3 ambient = (m.color * splat(1.0f)) * 0.08f;
-            const float df = attenuation(t);
-            const float3 direct = (ambient + sum_d) * df;
-            const float3 specular = sum_s * df;
-            const float3 local = m.transmissive ? specular : (direct + specular);
-            p.samples[sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+#ifdef RT_DBG_TAIL
+        {
+            int mx = n_cand < 0 ? 255 : n_cand;
+            for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+            dbg_cur_info |= (unsigned long long)(mx & 0xFF) | ((unsigned long long)(share ? 1 : 0) << 8);
         }
+#endif
+        if (!share) {
+            // every lane shades its own sample against the group's light copies, in order
+            if (r.hit) {
+                for (uint32_t l = 0; l < n_in_group; l++) {
+                    float3 dc, spc;
+                    if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
+                    const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
+                    shade_pair<COUNT, BEAM ? 1 : 0>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
+                                                    &last_occluder);
+                    sum_d = sum_d + dc;
+                    sum_s = sum_s + spc;
+                }
+            }
+        } else if (SHARE && BEAM) {
+            LightSums in;
+            in.d = sum_d;
+            in.s = sum_s;
+            const LightSums out = run_published_unit<COUNT>(gp, hq, hscratch, unit, warp_id, r.hit, r.P, r.N, r.d, r.mcolor, r.mshininess, L.pos, L.intensity,
+                                                            L.color, cloud, cand, n_cand, in, COUNT ? &cn : nullptr);
+            sum_d = out.d;
+            sum_s = out.s;
+        }
+#ifdef RT_DBG_TAIL
+        {
+            const unsigned long long now = dbg_globaltimer();
+            if (now - dbg_last_start > dbg_worst) {
+                dbg_worst = now - dbg_last_start;
+                dbg_worst_info = dbg_cur_info;
+                dbg_ph0 = dbg_tb - dbg_last_start;  // rebuild + chain wait + beam
+                dbg_ph1 = now - dbg_tb;             // copies
+                dbg_ph2 = 0ull;
+            }
+        }
+#endif
+        if (r.hit) {
+            if (!last) {
+                const float tag = __uint_as_float(frame_tag + group_index);
+                st_relaxed_gpu(&state[item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+                st_relaxed_gpu(&state[item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+            } else {
+                // single_raytrace without bounces (raytracer_renderer.rs:195-257)
+                const float3 ambient = (r.mcolor * splat(1.0f)) * 0.08f;
+                const float df = attenuation(r.t);
+                const float3 direct = (ambient + sum_d) * df;
+                const float3 specular = sum_s * df;
+                const float3 local = r.transmissive ? specular : (direct + specular);
+                p.samples[r.sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+            }
+        } else if (r.valid && last) {
+            p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        if (SHARE && BEAM && sharing && lane == 0) atomicAdd(&hq->units_done, 1u);
+    }
+    // the queue is empty: help with published units until the frame is finished
+    if (SHARE && BEAM && sharing) {
+#ifdef RT_DBG_TAIL
+        const unsigned long long dbg_h0 = dbg_globaltimer();
+#endif
+        const uint32_t helped = help_until_done<COUNT>(gp, hq, hscratch, n_units, n_batches, COUNT ? &cn : nullptr);
+#ifdef RT_DBG_TAIL
+        dbg_helped += helped;
+        dbg_help_time += dbg_globaltimer() - dbg_h0;
+#else
+        (void)helped;
+#endif
     }
     if (COUNT) {
         atomicAdd(p.counters + 0, cn.closest);
@@ -621,6 +913,14 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_MIN_CTAS_PER_SM) direct_ker
         atomicAdd(p.counters + 4, cn.sph);
         atomicAdd(p.counters + 5, cn.beam_prim);
     }
+#ifdef RT_DBG_TAIL
+    if (lane == 0) {  // per warp: start, end, start of its last unit, time spent waiting on chained records, units
+        unsigned long long *o = g_dbg_tail + 12 * (size_t)warp_id;
+        o[8] = dbg_ph0; o[9] = dbg_ph1; o[10] = dbg_ph2; o[11] = dbg_help_time;
+        o[0] = dbg_t0; o[1] = dbg_globaltimer(); o[2] = dbg_last_start; o[3] = dbg_spin; o[4] = dbg_units; o[5] = dbg_worst; o[6] = dbg_worst_info;
+        o[7] = dbg_helped;
+    }
+#endif
 }
 
 // raw cloud points (K x M x [f32;3], as handed over) -> float4 table scaled to scene units, the
