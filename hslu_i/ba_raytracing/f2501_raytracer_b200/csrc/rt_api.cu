@@ -45,12 +45,14 @@ struct rt_scene {
     DirectState *direct_state = nullptr;  // running light sums between the passes of direct_kernel
     size_t direct_cap = 0;
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
-    HelpQueue *help_queue = nullptr;        // publication queue of very expensive units (direct_kernel)
+    HeavyQueue *heavy_queue = nullptr;      // list of deferred (very expensive) units of direct_kernel
     RenderParams *d_params = nullptr;       // global-memory copy of the kernel parameters for direct_kernel's out-of-line paths
     RenderParams *h_params = nullptr;       // pinned staging buffers of it (ring: a copy must outlive its async upload)
     uint32_t h_params_next = 0;
-    float4 *help_scratch = nullptr;         // per owner warp: M copies x 32 samples x 2 float4
-    size_t help_scratch_cap = 0;
+    unsigned int *h_watchdog = nullptr;     // pinned: HeavyQueue::watchdog of the last frame
+    bool frame_has_watchdog = false;
+    float4 *heavy_scratch = nullptr;        // per deferred unit: M copies x 32 samples x 2 float4
+    size_t heavy_scratch_cap = 0;
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
     float *clouds_raw = nullptr;  // K x M x 3 cloud points, as handed over
@@ -221,6 +223,7 @@ static int select_device(int device) {
 static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, uint32_t *d_argb, uint8_t *d_mask, cudaStream_t stream,
                           uint64_t *launches) {
     fill_params(s, cfg, p);
+    s->frame_has_watchdog = false;
     if (p.LM > 0 && p.M > 1) {
         const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
         const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
@@ -302,7 +305,8 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
         {
             const size_t before = s->direct_cap;
-            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>(p.n_items, 1) * sizeof(DirectState));
+            // one chained record per (light group, sample); the last group writes the sample itself
+            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)warps_needed * 32 * (passes > 1 ? passes - 1 : 1), 1) * sizeof(DirectState));
             if (rc) return rc;
             if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
         }
@@ -316,7 +320,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         }
         // tags of this frame's chained records: never equal to a tag left in the buffer by an earlier frame
         s->frame_serial += MAX_PASSES;
-        if (s->frame_serial > 0xFFFF0000u) {
+        if (s->frame_serial > 0x7FFF0000u) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
             CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
             s->frame_serial = MAX_PASSES;
         }
@@ -324,26 +328,26 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
                            std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
         // few units per warp (a rank's share of a multi-GPU frame): the tail of the launch matters more than the
-        // last 6 % of steady-state throughput -> the variant that shares very expensive units between warps
+        // last few per cent of steady-state throughput -> the variant that defers very expensive units
         const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / ((uint64_t)dgrid * CTA_WARPS));
-        uint32_t share_below = 100;
-        if (const char *e = getenv("RT_SHARE_BELOW")) share_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
-        const bool share = beams && pd.M <= 32 && (size_t)dgrid * CTA_WARPS <= HELP_MAX_WARPS && units_per_warp < share_below;
-        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HelpQueue *, float4 *, const RenderParams *);
+        uint32_t defer_below = 100;
+        if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
+        const bool defer = beams && units_per_warp < defer_below;
+        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *);
         kernel_t kernel;
         if (count)
-            kernel = beams ? (share ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
+            kernel = beams ? (defer ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
         else
-            kernel = beams ? (share ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
-        HelpQueue *hq = nullptr;
-        if (share) {
-            if (!s->help_queue) CU_CHECK(cudaMalloc((void **)&s->help_queue, sizeof(HelpQueue)));
-            rc = grow(s->help_scratch, s->help_scratch_cap, (size_t)dgrid * CTA_WARPS * pd.M * 32 * 2 * sizeof(float4));
+            kernel = beams ? (defer ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
+        HeavyQueue *hq = nullptr;
+        if (defer) {
+            if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
+            rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;
-            CU_CHECK(cudaMemsetAsync(s->help_queue, 0, sizeof(HelpQueue), stream));
-            hq = s->help_queue;
-        }
-        if (hq) {
+            CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, offsetof(HeavyQueue, unit), stream));
+            CU_CHECK(cudaMemsetAsync((char *)s->heavy_queue + offsetof(HeavyQueue, unit), 0xFF, sizeof(HeavyQueue) - offsetof(HeavyQueue, unit), stream));
+            hq = s->heavy_queue;
+            s->frame_has_watchdog = true;
             constexpr uint32_t RING = 16;
             if (!s->d_params) CU_CHECK(cudaMalloc((void **)&s->d_params, sizeof(RenderParams)));
             if (!s->h_params) CU_CHECK(cudaMallocHost((void **)&s->h_params, RING * sizeof(RenderParams)));
@@ -352,7 +356,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
         }
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state, hq, s->help_scratch, s->d_params);
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state, hq, s->heavy_scratch, s->d_params);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
@@ -362,6 +366,21 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask);
     CU_CHECK(cudaGetLastError());
     if (launches) *launches += 1;
+    return RT_OK;
+}
+
+// after the frame's kernels: fetch the device watchdog word (enqueue) / check it (after the stream is synchronised)
+static int enqueue_watchdog_fetch(rt_scene *s, cudaStream_t stream) {
+    if (!s->frame_has_watchdog) return RT_OK;
+    if (!s->h_watchdog) CU_CHECK(cudaMallocHost((void **)&s->h_watchdog, sizeof(unsigned int)));
+    *s->h_watchdog = 0;
+    CU_CHECK(cudaMemcpyAsync(s->h_watchdog, &s->heavy_queue->watchdog, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    return RT_OK;
+}
+static int check_watchdog(rt_scene *s) {
+    if (!s->frame_has_watchdog || !s->h_watchdog) return RT_OK;
+    s->frame_has_watchdog = false;
+    if (*s->h_watchdog) return rt_fail(RT_ERR_CUDA, "direct_kernel: a wait loop gave up (code %u); the frame is invalid", *s->h_watchdog);
     return RT_OK;
 }
 
@@ -507,10 +526,11 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->help_queue, s->help_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->h_params) cudaFreeHost(s->h_params);
+    if (s->h_watchdog) cudaFreeHost(s->h_watchdog);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
     if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -540,6 +560,9 @@ int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         CU_CHECK(cudaEventRecord(s->ev1, stream));
+        if ((rc = enqueue_watchdog_fetch(s, stream))) return rc;
+        CU_CHECK(cudaStreamSynchronize(stream));
+        if ((rc = check_watchdog(s))) return rc;
         CU_CHECK(cudaEventSynchronize(s->ev1));
         float ms = 0;
         CU_CHECK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -584,7 +607,9 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
         CU_CHECK(cudaMemcpyAsync(s->pinned_argb, s->slab_argb, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
         CU_CHECK(cudaMemcpyAsync(s->pinned_mask, s->slab_mask, n_pix, cudaMemcpyDeviceToHost, s->stream));
     }
+    if ((rc = enqueue_watchdog_fetch(s, s->stream))) return rc;
     CU_CHECK(cudaStreamSynchronize(s->stream));
+    if ((rc = check_watchdog(s))) return rc;
     // ImageBuffer semantics (reference src/renderer/mod.rs:116-125): only hit pixels are stored
     const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
     for (uint32_t lr = 0; lr < rows; lr++) {

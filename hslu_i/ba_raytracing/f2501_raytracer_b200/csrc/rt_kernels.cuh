@@ -522,26 +522,34 @@ RT_DEV unsigned long long dbg_globaltimer() {
 }
 #endif
 
-// ---- sharing of very expensive units ------------------------------------------------------------
-// A few units cost 20-30x the average: all 32 samples sit where the M shadow rays of one light run
-// lengthwise through dense geometry, their beams overflow and every ray walks the BVH itself.  One
-// such unit handed out late is the whole tail of the frame (and the chain keeps its successors
-// waiting).  Its owner therefore publishes it: the M copies become M independent sub-tasks (copy c
-// for all 32 samples) that warps pick up once the unit queue has run dry (the tail of the frame is
-// where it matters; polling between units would cost more than it gains).  Contributions go to a
-// scratch slab and the owner adds them up in copy order, so the result is bit-identical.
-constexpr uint32_t HELP_SLOTS = 64;        // publications open at the same time (more: the owner works alone)
-constexpr uint32_t HELP_MAX_WARPS = 8192;
-constexpr uint32_t HELP_CLOSED = 0x80000000u;
-struct HelpDesc {
-    unsigned int unit, next_copy, done, pad;
-};
-struct HelpQueue {
-    unsigned int units_done, pad0, pad1, pad2;
-    unsigned int open[HELP_SLOTS];  // owner warp + 1 of an open publication, 0 = free
-    HelpDesc desc[HELP_MAX_WARPS];  // per owner warp
+// ---- very expensive units ---------------------------------------------------------------------
+// A few units cost 20-30x the average: their samples sit where the M shadow rays of one light run
+// lengthwise through dense geometry, the beams overflow and every ray walks the BVH itself, while the
+// other lanes of the warp wait (SIMT).  Handed out late, one such unit is the tail of the whole launch
+// -- and with a rank's share of a multi-GPU frame every unit is "late".  They are therefore DEFERRED:
+// the unit is put on a list (and marked in the chain, so that the units that continue its samples'
+// sums defer themselves too), and once the unit queue has run dry all warps work the list off together:
+// one sub-task = one light copy for the 32 samples of a unit.  Contributions go to a scratch slab; the
+// warp that completes a unit's last sub-task adds them to the predecessor's sums in copy order, i.e.
+// in the reference's light order: the image is bit-identical to processing the unit in place.
+constexpr uint32_t HEAVY_CAP = 16384;             // deferred units per launch (beyond: processed in place)
+constexpr uint32_t CHAIN_DEFERRED = 0x80000000u;  // flag in a chain tag: the unit is on the heavy list
+struct HeavyQueue {
+    unsigned int n_heavy;       // units on the list
+    unsigned int next_task;     // next sub-task ticket: heavy index * M + copy
+    unsigned int warps_done_a;  // warps that have left the unit loop (after that the list is final)
+    unsigned int watchdog;      // != 0: a wait loop gave up (code of the loop); the frame is invalid
+    unsigned int done[HEAVY_CAP];  // finished sub-tasks
+    unsigned int unit[HEAVY_CAP];  // 0xFFFFFFFF until written (the host memsets this part to 0xFF, the rest to 0)
 };
 RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
+// Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render
+// fails with RT_ERR_CUDA), never as a hung GPU.
+constexpr uint32_t WAIT_SPINS = 1u << 23;   // plain polling loops (seconds)
+constexpr uint32_t WAIT_SLEEPS = 1u << 21;  // loops that sleep 1 us per poll (seconds)
+RT_DEV void watchdog_trip(HeavyQueue *hq, unsigned int code) {
+    if (hq) atomicMax(&hq->watchdog, code);
+}
 
 // one sample of a batch, rebuilt from the primary pre-pass record (cheap next to its shadow rays)
 struct SampleRec {
@@ -587,166 +595,147 @@ RT_DEV SampleRec rebuild_sample(const RenderParams &p, uint32_t item) {
     return r;
 }
 
-// The tail of direct_kernel: take copies of published units until every unit of the frame is finished.
-// Out of line (and reading the parameters from their global-memory copy) so that this rare path does not
-// weigh on the register allocation of the kernel's main loop.
+struct LightSums {  // running diffuse / specular light sums of one sample
+    float3 d, s;
+};
+// single_raytrace without bounces (raytracer_renderer.rs:195-257): the last light group publishes the sample
+RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float3 sum_d, float3 sum_s) {
+    const float3 ambient = (r.mcolor * splat(1.0f)) * 0.08f;
+    const float df = attenuation(r.t);
+    const float3 direct = (ambient + sum_d) * df;
+    const float3 specular = sum_s * df;
+    const float3 local = r.transmissive ? specular : (direct + specular);
+    p.samples[r.sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+}
+
+// Phase B of direct_kernel (see above).  Out of line, parameters read from their global-memory copy, so
+// that it does not weigh on the register allocation of the unit loop.
 template <bool COUNT>
-__device__ __noinline__ uint32_t help_until_done(const RenderParams *gp, HelpQueue *hq, float4 *hscratch, uint32_t n_units, uint32_t n_batches,
-                                                 Counters *cn_out) {
+__device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
+                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out) {
     const RenderParams &p = *gp;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
+    const uint32_t n_batches = (p.n_items + 31u) / 32u;
+    const size_t chain_stride = (size_t)n_batches * 32u;
     Counters cn = {0, 0, 0, 0, 0, 0};
-    uint32_t helped = 0;
+    if (lane == 0) atomicAdd(&hq->warps_done_a, 1u);
     for (;;) {
-        // (read first: once every unit is finished there is nothing left to help with)
-        const unsigned int finished = ld_volatile_u32(&hq->units_done);
-        if (finished >= n_units) break;
-        // every lane looks at two slots; owners of open publications are tried one after the other
-        const unsigned int e0 = ld_volatile_u32(&hq->open[lane]), e1 = ld_volatile_u32(&hq->open[lane + 32u]);
-        // (only publications that still have copies to hand out: no atomics on the exhausted ones)
-        const bool a0 = e0 != 0u && ld_volatile_u32(&hq->desc[e0 - 1u].next_copy) < p.M;
-        const bool a1 = e1 != 0u && ld_volatile_u32(&hq->desc[e1 - 1u].next_copy) < p.M;
-        unsigned m0 = __ballot_sync(FULL, a0), m1 = __ballot_sync(FULL, a1);
-        uint32_t h_unit = 0, h_copy = 0xFFFFFFFFu, h_owner = 0;
-        while ((m0 | m1) && h_copy == 0xFFFFFFFFu) {
-            const bool second = m0 == 0u;
-            const int src = __ffs(second ? m1 : m0) - 1;
-            if (second) m1 &= m1 - 1u; else m0 &= m0 - 1u;
-            const unsigned int e = __shfl_sync(FULL, second ? e1 : e0, src);
-            if (lane == 0) {
-                HelpDesc *ds = &hq->desc[e - 1u];
-                const unsigned int c = atomicAdd(&ds->next_copy, 1u);
-                if (c < p.M) {
-                    __threadfence();
-                    h_unit = ld_volatile_u32(&ds->unit);
-                    h_copy = c;
-                    h_owner = e - 1u;
-                }
-            }
-            h_copy = __shfl_sync(FULL, h_copy, 0);
-        }
-        if (h_copy == 0xFFFFFFFFu) {  // nothing to take right now: wait for the running units
-            __nanosleep(2000);
-            continue;
-        }
-        h_unit = __shfl_sync(FULL, h_unit, 0);
-        h_owner = __shfl_sync(FULL, h_owner, 0);
-        const uint32_t hg = h_unit / n_batches, hb = h_unit - hg * n_batches;
-        const SampleRec r = rebuild_sample(p, hb * 32u + lane);
-        if (r.hit) {
-            const LightCopy L = load_light(p, hg);
-            const uint32_t cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, hg, p.K);
-            float3 dc, spc;
-            shade_pair<COUNT, 2>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, copy_position(p, L.pos, cloud, h_copy), L.intensity, L.color, cull, cn, dc,
-                                 spc);
-            float4 *o = hscratch + (((size_t)h_owner * p.M + h_copy) * 32u + lane) * 2u;
-            st_relaxed_gpu(o, make_float4(dc.x, dc.y, dc.z, 0.0f));
-            st_relaxed_gpu(o + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
-        }
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(&hq->desc[h_owner].done, 1u);
-        helped++;
-    }
-    if (COUNT && cn_out) {
-        cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
-        cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
-    }
-    return helped;
-}
-
-struct LightSums {  // running diffuse / specular light sums of one sample
-    float3 d, s;
-};
-// The owner's side of a published unit (see above): hands out the M copies of its light one by one to
-// itself and to whoever helps, then adds the contributions up in copy order.  Out of line for the same
-// reason as help_until_done.
-template <bool COUNT>
-__device__ __noinline__ LightSums run_published_unit(const RenderParams *gp, HelpQueue *hq, float4 *hscratch, uint32_t unit, uint32_t warp_id, bool hit,
-                                                     float3 P, float3 N, float3 d, float3 mcolor, float mshininess, float3 lpos0, float lint, float3 lcol,
-                                                     uint32_t cloud, const uint32_t *cand, int n_cand, LightSums sums, Counters *cn_out) {
-    const RenderParams &p = *gp;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
-    Counters cn = {0, 0, 0, 0, 0, 0};
-    int32_t last_occluder = -1;
-    float3 sd = sums.d, ss = sums.s;
-    HelpDesc *ds = &hq->desc[warp_id];
-    int my_slot = -1;
-    if (lane == 0) {
-        atomicExch(&ds->next_copy, HELP_CLOSED);  // stale helpers of the previous publication see "nothing left"
-        __threadfence();
-        *(volatile unsigned int *)&ds->unit = unit;
-        *(volatile unsigned int *)&ds->done = 0u;
-        __threadfence();
-        atomicExch(&ds->next_copy, 0u);  // open
-        __threadfence();
-    }
-    __syncwarp();
-    for (;;) {  // the owner works on its own publication like any helper (but keeps its beam lists)
-        uint32_t c = 0;
+        // tickets are handed out in list order; one that is ahead of the list waits until the list has grown
+        // that far or is final (every warp has left the unit loop)
+        uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0;
         if (lane == 0) {
-            // make the publication visible in a free slot of the table (tried again before every copy:
-            // the table may be full in the middle of the frame, it never is at its tail)
-            for (uint32_t k = 0; k < 4u && my_slot < 0; k++) {
-                const uint32_t idx = (warp_id * 7u + k * 13u + ld_volatile_u32(&ds->next_copy)) % HELP_SLOTS;
-                if (ld_volatile_u32(&hq->open[idx]) == 0u && atomicCAS(&hq->open[idx], 0u, warp_id + 1u) == 0u) my_slot = (int)idx;
+            const unsigned int t = atomicAdd(&hq->next_task, 1u);
+            const uint32_t want = t / p.M;
+            for (uint32_t spins = 0;; spins++) {
+                if (spins > WAIT_SLEEPS) {
+                    watchdog_trip(hq, 1u);
+                    break;
+                }
+                const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
+                const unsigned int n = min(ld_volatile_u32(&hq->n_heavy), HEAVY_CAP);
+                if (want < n) {
+                    idx = want;
+                    c = t - want * p.M;
+                    for (uint32_t w = 0; (unit = ld_volatile_u32(&hq->unit[idx])) == 0xFFFFFFFFu; w++)
+                        if (w > WAIT_SPINS) {
+                            watchdog_trip(hq, 2u);
+                            idx = 0xFFFFFFFFu;
+                            break;
+                        }
+                    break;
+                }
+                if (final_list) break;
+                __nanosleep(1000);
             }
-            c = atomicAdd(&ds->next_copy, 1u);
         }
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx == 0xFFFFFFFFu) break;
         c = __shfl_sync(FULL, c, 0);
-        if (c >= p.M) break;
-        if (hit) {
+        unit = __shfl_sync(FULL, unit, 0);
+        const uint32_t g = unit / n_batches, b = unit - g * n_batches;
+        const uint32_t item = b * 32u + lane;
+        const SampleRec r = rebuild_sample(p, item);
+        float4 *slab = hscratch + ((size_t)idx * p.M * 32u + lane) * 2u;  // + copy * 64
+        if (r.hit) {
+            const LightCopy L = load_light(p, g);
+            const uint32_t cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, g, p.K);
             float3 dc, spc;
-            shade_pair<COUNT, 1>(p, P, N, d, mcolor, mshininess, copy_position(p, lpos0, cloud, c), lint, lcol, cull, cn, dc, spc,
-                                 cand, n_cand, &last_occluder);
-            float4 *o = hscratch + (((size_t)warp_id * p.M + c) * 32u + lane) * 2u;
-            st_relaxed_gpu(o, make_float4(dc.x, dc.y, dc.z, 0.0f));
-            st_relaxed_gpu(o + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
+            shade_pair<COUNT, 2>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, copy_position(p, L.pos, cloud, c), L.intensity, L.color, cull, cn, dc, spc);
+            st_relaxed_gpu(slab + (size_t)c * 64u, make_float4(dc.x, dc.y, dc.z, 0.0f));
+            st_relaxed_gpu(slab + (size_t)c * 64u + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
         }
         __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(&ds->done, 1u);
-    }
-    if (lane == 0) {
-        while (ld_volatile_u32(&ds->done) < p.M) {
-        }
-        if (my_slot >= 0) atomicExch(&hq->open[my_slot], 0u);
-    }
-    __syncwarp();
-    __threadfence();
-    if (hit) {
-        for (uint32_t c = 0; c < p.M; c++) {  // copy order = the reference's light order
-            const float4 *o = hscratch + (((size_t)warp_id * p.M + c) * 32u + lane) * 2u;
-            const float4 a = ld_relaxed_gpu(o), b2 = ld_relaxed_gpu(o + 1);
-            sd = sd + f3(a.x, a.y, a.z);
-            ss = ss + f3(b2.x, b2.y, b2.z);
+        unsigned int finished = 0;
+        if (lane == 0) finished = atomicAdd(&hq->done[idx], 1u) + 1u;
+        finished = __shfl_sync(FULL, finished, 0);
+        if (finished != p.M) continue;
+        // last sub-task of the unit: continue the predecessor's sums with the M contributions, in copy order
+        __threadfence();
+        if (r.hit) {
+            float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
+            if (g > 0) {
+                const uint32_t want = frame_tag + g - 1u;  // (a deferred predecessor is further up the list: being worked on)
+                float4 sd, ss;
+                uint32_t spins = 0;
+                do {
+                    sd = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].d);
+                    ss = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].s);
+                    if (++spins > WAIT_SPINS) {
+                        watchdog_trip(hq, 3u);
+                        break;
+                    }
+                } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
+                sum_d = f3(sd.x, sd.y, sd.z);
+                sum_s = f3(ss.x, ss.y, ss.z);
+            }
+            for (uint32_t k = 0; k < p.M; k++) {
+                const float4 a = ld_relaxed_gpu(slab + (size_t)k * 64u), b2 = ld_relaxed_gpu(slab + (size_t)k * 64u + 1);
+                sum_d = sum_d + f3(a.x, a.y, a.z);
+                sum_s = sum_s + f3(b2.x, b2.y, b2.z);
+            }
+            if (g + 1 != n_groups) {
+                const float tag = __uint_as_float(frame_tag + g);
+                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+            } else {
+                store_direct_sample(p, r, sum_d, sum_s);
+            }
         }
     }
     if (COUNT && cn_out) {
         cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
         cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
     }
-    sums.d = sd;
-    sums.s = ss;
-    return sums;
 }
 
-#ifndef RT_SHARE_MODE
-#define RT_SHARE_MODE 2  // 0: units are never shared, 1: when most samples of the batch overflowed, 2: when any did
-#endif
 #ifndef RT_DIRECT_MIN_CTAS
 #define RT_DIRECT_MIN_CTAS RT_MIN_CTAS_PER_SM
 #endif
-// SHARE: with the publication machinery (costs ~6 % of steady-state throughput, cuts the tail of the frame
-// from ~0.5 ms to ~0.1 ms): chosen by the host when a launch has few units per warp (multi-GPU tiles).
-template <bool COUNT, bool BEAM, bool SHARE>
+// puts `unit` on the heavy list (slot idx): marks its chain records so that the units that continue these
+// samples' sums defer themselves too, zeroes the samples of lanes that missed (last group), publishes
+__device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, float4 *sample, uint32_t unit, uint32_t idx, uint32_t deferred_tag,
+                                        bool mark_chain, bool zero_sample) {
+    if (mark_chain) {
+        const float tag = __uint_as_float(deferred_tag);
+        st_relaxed_gpu(&own_rec->d, make_float4(0.0f, 0.0f, 0.0f, tag));
+        st_relaxed_gpu(&own_rec->s, make_float4(0.0f, 0.0f, 0.0f, tag));
+    }
+    if (zero_sample) *sample = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    __threadfence();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) *(volatile unsigned int *)&hq->unit[idx] = unit;
+}
+
+// DEFER: with the deferral of very expensive units compiled in.  It costs a few per cent of steady-state
+// throughput (register pressure in the unit loop) and removes the tail of the launch, so the host selects
+// it when a launch has few units per warp -- a rank's share of a multi-GPU frame.
+template <bool COUNT, bool BEAM, bool DEFER>
 __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
-                                                                                    unsigned int *counter, DirectState *state, HelpQueue *hq,
+                                                                                    unsigned int *counter, DirectState *state, HeavyQueue *hq,
                                                                                     float4 *hscratch, const RenderParams *gp) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -755,10 +744,11 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
-    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const bool sharing = SHARE && BEAM && hq != nullptr && p.M <= 32u && warp_id < HELP_MAX_WARPS;
+    const size_t chain_stride = (size_t)n_batches * 32u;  // one record per (group, sample): a record is never overwritten by a later group
+    const bool deferring = DEFER && BEAM && hq != nullptr;
     Counters cn = {0, 0, 0, 0, 0, 0};
 #ifdef RT_DBG_TAIL
+    const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long dbg_t0 = dbg_globaltimer(), dbg_spin = 0, dbg_last_start = 0, dbg_worst = 0, dbg_worst_info = 0, dbg_cur_info = 0;
     unsigned long long dbg_ph0 = 0, dbg_ph1 = 0, dbg_ph2 = 0, dbg_help_time = 0;
     uint32_t dbg_units = 0, dbg_helped = 0;
@@ -777,6 +767,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
         const bool last = group_index + 1 == n_groups;
         const uint32_t item = batch * 32u + lane;
         const SampleRec r = rebuild_sample(p, item);
+        DirectState *const own_rec = state + (size_t)group_index * chain_stride + item;
+        const DirectState *const prev_rec = own_rec - chain_stride;  // (only dereferenced when group_index > 0)
         if (COUNT && r.valid && group_index == 0) cn.closest++;
         // lanes of a batch that missed sit the batch out but stay with the warp
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
@@ -786,6 +778,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
         uint32_t cand[BEAM_MAX_CAND];  // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
         int n_cand = -1;
         int32_t last_occluder = -1;
+        bool defer = false;  // this lane wants the unit deferred
         LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
         if (p.LM > 0) L = load_light(p, li0);
         if (r.hit) {
@@ -796,10 +789,20 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
 #ifdef RT_DBG_TAIL
                 const unsigned long long dbg_s0 = dbg_globaltimer();
 #endif
-                do {
-                    sd = ld_relaxed_gpu(&state[item].d);
-                    ss = ld_relaxed_gpu(&state[item].s);
-                } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
+                for (uint32_t spins = 0;; spins++) {
+                    if (spins > WAIT_SPINS) {
+                        watchdog_trip(hq, 4u);
+                        break;
+                    }
+                    sd = ld_relaxed_gpu(&prev_rec->d);
+                    ss = ld_relaxed_gpu(&prev_rec->s);
+                    const uint32_t td = __float_as_uint(sd.w), ts = __float_as_uint(ss.w);
+                    if (td == want && ts == want) break;
+                    if (DEFER && td == (want | CHAIN_DEFERRED)) {  // the predecessor is on the heavy list: so is this unit
+                        defer = true;
+                        break;
+                    }
+                }
 #ifdef RT_DBG_TAIL
                 dbg_spin += dbg_globaltimer() - dbg_s0;
 #endif
@@ -807,7 +810,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
                 sum_s = f3(ss.x, ss.y, ss.z);
             }
             if (p.M > 1) cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, li0, p.K);
-            if (BEAM) {
+            if (BEAM && !defer) {
                 const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
                 // the same float operations as the copies' `lpos + rp * w2s`, which are monotonic in rp
                 const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
@@ -816,50 +819,61 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
                 const Beam beam = make_beam(r.P, lmin, lmax, pad);
                 const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
                 n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn);
+                if (DEFER) defer = n_cand < 0;  // overflow: M separate BVH walks, everybody else in the warp waiting
+            }
+        }
+        if (DEFER && BEAM && deferring) {
+            __syncwarp();
+            const unsigned want_defer = __ballot_sync(FULL, defer);
+            if (want_defer) {
+                unsigned int idx = 0;
+                if (lane == 0) idx = atomicAdd(&hq->n_heavy, 1u);
+                idx = __shfl_sync(FULL, idx, 0);
+                if (idx < HEAVY_CAP) {
+                    defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (frame_tag + group_index) | CHAIN_DEFERRED, !last && r.hit,
+                               last && r.valid && !r.hit);
+#ifdef RT_DBG_TAIL
+                    dbg_helped++;
+#endif
+                    continue;
+                }
+                // the list is full: process in place (a deferred predecessor is finished by phase B: wait for it)
+                if (r.hit && group_index > 0) {
+                    const uint32_t want = frame_tag + group_index - 1u;
+                    float4 sd, ss;
+                    uint32_t spins = 0;
+                    do {
+                        sd = ld_relaxed_gpu(&prev_rec->d);
+                        ss = ld_relaxed_gpu(&prev_rec->s);
+                        if (++spins > WAIT_SPINS) {
+                            watchdog_trip(hq, 5u);
+                            break;
+                        }
+                    } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
+                    sum_d = f3(sd.x, sd.y, sd.z);
+                    sum_s = f3(ss.x, ss.y, ss.z);
+                }
             }
         }
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_tb = dbg_globaltimer();
-#endif
-        bool share = false;
-        if (SHARE && BEAM && sharing) {
-            // some sample's beam overflowed: its M rays walk the BVH one by one and the whole warp waits for
-            // them (SIMT), so the unit costs the same whoever traces the other lanes -- publish the copies
-            __syncwarp();
-#if RT_SHARE_MODE == 1
-            share = 2 * __popc(__ballot_sync(FULL, r.hit && n_cand < 0)) > __popc(__ballot_sync(FULL, r.hit));
-#else
-            share = __ballot_sync(FULL, r.hit && n_cand < 0) != 0u;
-#endif
-        }
-#ifdef RT_DBG_TAIL
         {
             int mx = n_cand < 0 ? 255 : n_cand;
             for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-            dbg_cur_info |= (unsigned long long)(mx & 0xFF) | ((unsigned long long)(share ? 1 : 0) << 8);
+            dbg_cur_info |= (unsigned long long)(mx & 0xFF);
         }
 #endif
-        if (!share) {
-            // every lane shades its own sample against the group's light copies, in order
-            if (r.hit) {
-                for (uint32_t l = 0; l < n_in_group; l++) {
-                    float3 dc, spc;
-                    if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
-                    const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
-                    shade_pair<COUNT, BEAM ? 1 : 0>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
-                                                    &last_occluder);
-                    sum_d = sum_d + dc;
-                    sum_s = sum_s + spc;
-                }
+        // every lane shades its own sample against the group's light copies, in order
+        if (r.hit) {
+            for (uint32_t l = 0; l < n_in_group; l++) {
+                float3 dc, spc;
+                if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
+                const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
+                shade_pair<COUNT, BEAM ? 1 : 0>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
+                                                &last_occluder);
+                sum_d = sum_d + dc;
+                sum_s = sum_s + spc;
             }
-        } else if (SHARE && BEAM) {
-            LightSums in;
-            in.d = sum_d;
-            in.s = sum_s;
-            const LightSums out = run_published_unit<COUNT>(gp, hq, hscratch, unit, warp_id, r.hit, r.P, r.N, r.d, r.mcolor, r.mshininess, L.pos, L.intensity,
-                                                            L.color, cloud, cand, n_cand, in, COUNT ? &cn : nullptr);
-            sum_d = out.d;
-            sum_s = out.s;
         }
 #ifdef RT_DBG_TAIL
         {
@@ -876,33 +890,23 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_ker
         if (r.hit) {
             if (!last) {
                 const float tag = __uint_as_float(frame_tag + group_index);
-                st_relaxed_gpu(&state[item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
-                st_relaxed_gpu(&state[item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+                st_relaxed_gpu(&own_rec->d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+                st_relaxed_gpu(&own_rec->s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
             } else {
-                // single_raytrace without bounces (raytracer_renderer.rs:195-257)
-                const float3 ambient = (r.mcolor * splat(1.0f)) * 0.08f;
-                const float df = attenuation(r.t);
-                const float3 direct = (ambient + sum_d) * df;
-                const float3 specular = sum_s * df;
-                const float3 local = r.transmissive ? specular : (direct + specular);
-                p.samples[r.sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+                store_direct_sample(p, r, sum_d, sum_s);
             }
         } else if (r.valid && last) {
             p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
-        if (SHARE && BEAM && sharing && lane == 0) atomicAdd(&hq->units_done, 1u);
     }
-    // the queue is empty: help with published units until the frame is finished
-    if (SHARE && BEAM && sharing) {
+    // the queue is empty: work off the deferred units together
+    if (DEFER && BEAM && deferring) {
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        const uint32_t helped = help_until_done<COUNT>(gp, hq, hscratch, n_units, n_batches, COUNT ? &cn : nullptr);
+        finish_heavy_units<COUNT>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr);
 #ifdef RT_DBG_TAIL
-        dbg_helped += helped;
         dbg_help_time += dbg_globaltimer() - dbg_h0;
-#else
-        (void)helped;
 #endif
     }
     if (COUNT) {

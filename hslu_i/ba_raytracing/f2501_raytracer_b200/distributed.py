@@ -16,7 +16,7 @@ import ctypes as C
 from . import _lib as L
 from .renderer import DeviceScene, RenderConfig
 
-DEFAULT_TILE_ROWS = 8
+DEFAULT_TILE_ROWS = 2  # fine interleave: ranks' costs within ~2 % of each other on the headline frame (tools/gpu_tiles_onegpu.py)
 
 
 def padded_rows(rc: RenderConfig, tile_rows: int, world: int) -> int:

@@ -300,3 +300,66 @@ def test_renderer_api_mirror(pkg, oracle_mod):
     mask = np.zeros(768 * 640, np.uint8)
     pkg._lib.check(lib.rth_render(scene._h, b"backface_culling", 0, 0, pkg._lib.ptr(out), pkg._lib.ptr(mask), None))
     assert np.array_equal(out, buf.buffer) and np.array_equal(mask, buf.hit_mask)
+
+
+# ---------------------------------------------------------------- shadow beams / unit sharing / tile placement
+@pytest.mark.parametrize("scene_name,features,kw", [
+    ("semesterbild", "high_quality,simd_render", dict(width=384, height=320, n_light_clouds=512)),
+    ("semesterbild", "high_quality", dict(width=256, height=214, n_light_clouds=64)),
+    ("test_scene", "simd_render,backface_culling,soft_shadows", dict(width=570, height=475)),
+])
+def test_shadow_beams_equal_per_ray_traversal(pkg, scenes, scene_name, features, kw):
+    """One BVH walk per (shading point, light) for all M soft-shadow copies (shadow beams, the default)
+    must give the image of one walk per shadow ray bit for bit, with the same ray counts and fewer tests."""
+    L = pkg._lib
+    flat, dev = scenes(scene_name, features)
+    beam, _ = dev.render(pkg.RenderConfig.from_features(features, 5, **kw))
+    ray, _ = dev.render(pkg.RenderConfig.from_features(features, 5, extra_flags=L.FLAG_PER_RAY_SHADOWS, **kw))
+    assert np.array_equal(beam.buffer, ray.buffer) and np.array_equal(beam.hit_mask, ray.hit_mask)
+    _, sb = dev.render(pkg.RenderConfig.from_features(features, 5, extra_flags=L.FLAG_COUNT_WORK, **kw))
+    _, sr = dev.render(pkg.RenderConfig.from_features(features, 5, extra_flags=L.FLAG_COUNT_WORK | L.FLAG_PER_RAY_SHADOWS, **kw))
+    assert (sb["closest_rays"], sb["shadow_rays"]) == (sr["closest_rays"], sr["shadow_rays"])
+    assert sr["beam_triangle_tests"] == 0 and sb["beam_triangle_tests"] > 0
+    assert sb["box_tests"] < sr["box_tests"] / 4 and sb["triangle_tests"] < sr["triangle_tests"]
+
+
+def test_deferred_units_are_bit_identical(pkg, scenes, monkeypatch):
+    """direct_kernel defers very expensive units (overflowed beams) and lets all warps finish them together
+    at the end of the launch, adding the contributions in copy order: same image as processing in place."""
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 2).with_tiles(8, 5, 8)   # one rank's eighth of the headline frame
+    monkeypatch.setenv("RT_DEFER_BELOW", "1000000")  # always the deferring variant
+    a, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    monkeypatch.setenv("RT_DEFER_BELOW", "0")        # never
+    b, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    assert a.hit_mask.any() and np.array_equal(a.buffer, b.buffer) and np.array_equal(a.hit_mask, b.hit_mask)
+
+
+def test_place_tiles_and_kernel_times(pkg, scenes):
+    """rt_place_tiles: all ranks' gathered slabs -> frame + hit mask in one launch (mask = pixel != 0);
+    rt_kernel_times: one duration per render call."""
+    torch = pytest.importorskip("torch")
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import TiledRenderer, padded_rows
+
+    flat, dev = scenes("main", "")
+    rc = pkg.RenderConfig.from_features("", 0)
+    host, _ = dev.render(pkg.RenderConfig.from_features("", 0, extra_flags=pkg._lib.FLAG_ZERO_MISSES))
+    world, tile_rows = 5, 3
+    W, H = rc.cfg.width, rc.cfg.height
+    pad = padded_rows(rc, tile_rows, world)
+    gathered = torch.zeros(world * pad * W, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        tr = TiledRenderer(dev, rc, r, world, tile_rows=tile_rows)
+        tr.render_local()
+        gathered.view(world, -1)[r].copy_(tr.slab)
+    frame = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+    mask = torch.full((W * H,), 7, dtype=torch.uint8, device="cuda")
+    lib = pkg._lib.load()
+    cfg = rc.with_tiles(tile_rows, 0, world).cfg
+    pkg._lib.check(lib.rt_place_tiles(C.byref(cfg), gathered.data_ptr(), pad * W, frame.data_ptr(), mask.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(frame.cpu().numpy().view(np.uint32), host.buffer)
+    assert np.array_equal(mask.cpu().numpy(), host.hit_mask)
+    times = dev.kernel_times(world)
+    assert len(times) == world and (times > 0).all()

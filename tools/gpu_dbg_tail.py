@@ -39,8 +39,8 @@ for world, r in ((1, 0), (8, 0)):
     print("  warp end us    :", q(end))
     print("  last unit len  :", q(end - last))
     print("  spin us / warp :", q(spin), "total spin share", round(float(spin.sum() / (end - start).sum()), 4))
-    print("  units / warp   :", q(units), " helped sub-tasks total", int(out[:, 7].sum()),
-          "help-phase us / warp:", q(out[:, 11].astype(np.float64) / 1e3), flush=True)
+    print("  units / warp   :", q(units), " deferred units total", int(out[:, 7].sum()),
+          "phase-B us / warp:", q(out[:, 11].astype(np.float64) / 1e3), flush=True)
     worst = out[:, 5].astype(np.float64) / 1e3
     order = np.argsort(-worst)[:3]
     n_items = rcr.local_rows() * W * 16
