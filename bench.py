@@ -359,7 +359,15 @@ def main() -> None:
         kernel_ms = dom_ms_max                    # the dominant kernel's own launch duration (max over ranks of the per-rank mean)
         render_ms = kern_ms_max / args.steps      # primary + dominant + resolve kernels
         bounces = bool(rc.cfg.flags & (L.FLAG_REFLECTIONS | L.FLAG_REFRACTIONS))
-        dominant_kernel = "render_kernel<false>" if bounces else ("direct_kernel<false,true>" if rc.cfg.light_multiplicator > 1 else "direct_kernel<false,false>")
+        if bounces:
+            dominant_kernel = "render_kernel<false>"
+        elif rc.cfg.light_multiplicator > 1:
+            # rt_api.cu picks the DEFER variant for launches with < 100 units per resident warp
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            units = -(-tiled.rows * rc.cfg.width * rc.samples_per_pixel // 32) * len(flat.lights)
+            dominant_kernel = f"direct_kernel<false,true,{'true' if units // (sms * 7 * 4) < 100 else 'false'}>"
+        else:
+            dominant_kernel = "direct_kernel<false,false,false>"
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
             tj = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(args.workload)
