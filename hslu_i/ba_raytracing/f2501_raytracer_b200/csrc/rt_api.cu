@@ -49,12 +49,15 @@ struct rt_scene {
     RenderParams *d_params = nullptr;       // global-memory copy of the kernel parameters for direct_kernel's out-of-line paths
     RenderParams *h_params = nullptr;       // pinned staging buffers of it (ring: a copy must outlive its async upload)
     uint32_t h_params_next = 0;
+    RenderParams d_params_host{};           // what d_params currently holds
+    bool d_params_valid = false;
     unsigned int *h_watchdog = nullptr;     // pinned: HeavyQueue::watchdog of the last frame
     bool frame_has_watchdog = false;
     float4 *heavy_scratch = nullptr;        // per deferred unit: M copies x 32 samples x 2 float4
     size_t heavy_scratch_cap = 0;
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
+    int direct_ctas_per_sm[6] = {0, 0, 0, 0, 0, 0};  // per direct_kernel variant, filled on first use
     float *clouds_raw = nullptr;  // K x M x 3 cloud points, as handed over
     float4 *clouds = nullptr;     // the same points scaled to scene units (scale_clouds_kernel)
     size_t clouds_raw_cap = 0, clouds_cap = 0;
@@ -271,7 +274,6 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     p.work_counter = s->work_counter;
     p.counters = s->counters;
     if (p.local_rows == 0) return RT_OK;
-    CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
     const bool count = (cfg->flags & RT_FLAG_COUNT_WORK) != 0;
     if (count) CU_CHECK(cudaMemsetAsync(s->counters, 0, 16 * sizeof(unsigned long long), stream));
     int grid = s->sm_count * (count ? s->ctas_per_sm_count : s->ctas_per_sm);
@@ -289,6 +291,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     if (launches) *launches += 1;
     if (bounces) {
         // per-sample reflection / refraction trees: persistent megakernel
+        CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
         if (count)
             render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
@@ -310,9 +313,6 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             if (rc) return rc;
             if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
         }
-        CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
-        int dgrid = s->sm_count * (count ? s->ctas_per_sm_direct_count : s->ctas_per_sm_direct);
-        dgrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)dgrid, (warps_needed * passes + CTA_WARPS - 1) / CTA_WARPS));
         RenderParams pd = p;
         if (n_groups == 0) {  // no lights: ambient term only
             pd.LM = 0;
@@ -329,7 +329,8 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
                            std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
         // few units per warp (a rank's share of a multi-GPU frame): the tail of the launch matters more than the
         // last few per cent of steady-state throughput -> the variant that defers very expensive units
-        const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / ((uint64_t)dgrid * CTA_WARPS));
+        const uint32_t resident_warps = (uint32_t)s->sm_count * (uint32_t)std::max(s->ctas_per_sm_direct, 1) * CTA_WARPS;
+        const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / resident_warps);
         uint32_t defer_below = 100;
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
@@ -339,24 +340,38 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             kernel = beams ? (defer ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
         else
             kernel = beams ? (defer ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
+        // persistent grid: SMs x resident CTAs of the selected variant (they differ in register budget)
+        const int variant = (count ? 3 : 0) + (beams ? (defer ? 2 : 1) : 0);
+        if (s->direct_ctas_per_sm[variant] == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+            s->direct_ctas_per_sm[variant] = n;
+        }
+        int dgrid = s->sm_count * s->direct_ctas_per_sm[variant];
+        dgrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)dgrid, (warps_needed * passes + CTA_WARPS - 1) / CTA_WARPS));
         HeavyQueue *hq = nullptr;
         if (defer) {
             if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
             rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;
-            CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, offsetof(HeavyQueue, unit), stream));
-            CU_CHECK(cudaMemsetAsync((char *)s->heavy_queue + offsetof(HeavyQueue, unit), 0xFF, sizeof(HeavyQueue) - offsetof(HeavyQueue, unit), stream));
+            CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter
             hq = s->heavy_queue;
             s->frame_has_watchdog = true;
             constexpr uint32_t RING = 16;
             if (!s->d_params) CU_CHECK(cudaMalloc((void **)&s->d_params, sizeof(RenderParams)));
             if (!s->h_params) CU_CHECK(cudaMallocHost((void **)&s->h_params, RING * sizeof(RenderParams)));
-            RenderParams *stage = s->h_params + (s->h_params_next++ % RING);
-            *stage = pd;
-            CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
+            if (!s->d_params_valid || memcmp(&s->d_params_host, &pd, sizeof(RenderParams)) != 0) {  // steady state: nothing to upload
+                RenderParams *stage = s->h_params + (s->h_params_next++ % RING);
+                *stage = pd;
+                CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
+                s->d_params_host = pd;
+                s->d_params_valid = true;
+            }
         }
+        unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
+        if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, s->pass_counters, s->direct_state, hq, s->heavy_scratch, s->d_params);
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
@@ -511,9 +526,9 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
         s->ctas_per_sm_count = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true, false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
         s->ctas_per_sm_direct = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true, true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct_count, direct_kernel<true, true, false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct_count < 1)
         s->ctas_per_sm_direct_count = 1;
     if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||

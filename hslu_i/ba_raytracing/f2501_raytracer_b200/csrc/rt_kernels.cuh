@@ -539,8 +539,10 @@ struct HeavyQueue {
     unsigned int next_task;     // next sub-task ticket: heavy index * M + copy
     unsigned int warps_done_a;  // warps that have left the unit loop (after that the list is final)
     unsigned int watchdog;      // != 0: a wait loop gave up (code of the loop); the frame is invalid
+    unsigned int unit_counter;  // direct_kernel's unit queue (here so that one memset resets everything)
+    unsigned int pad[3];
     unsigned int done[HEAVY_CAP];  // finished sub-tasks
-    unsigned int unit[HEAVY_CAP];  // 0xFFFFFFFF until written (the host memsets this part to 0xFF, the rest to 0)
+    unsigned int unit[HEAVY_CAP];  // unit + 1; 0 until written
 };
 RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
 // Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render
@@ -639,7 +641,7 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                 if (want < n) {
                     idx = want;
                     c = t - want * p.M;
-                    for (uint32_t w = 0; (unit = ld_volatile_u32(&hq->unit[idx])) == 0xFFFFFFFFu; w++)
+                    for (uint32_t w = 0; (unit = ld_volatile_u32(&hq->unit[idx]) - 1u) == 0xFFFFFFFFu; w++)
                         if (w > WAIT_SPINS) {
                             watchdog_trip(hq, 2u);
                             idx = 0xFFFFFFFFu;
@@ -727,14 +729,17 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
     if (zero_sample) *sample = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __threadfence();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) *(volatile unsigned int *)&hq->unit[idx] = unit;
+    if ((threadIdx.x & 31) == 0) *(volatile unsigned int *)&hq->unit[idx] = unit + 1u;
 }
 
 // DEFER: with the deferral of very expensive units compiled in.  It costs a few per cent of steady-state
 // throughput (register pressure in the unit loop) and removes the tail of the launch, so the host selects
 // it when a launch has few units per warp -- a rank's share of a multi-GPU frame.
+#ifndef RT_DEFER_MIN_CTAS
+#define RT_DEFER_MIN_CTAS 6  // the DEFER variant is better off with 80 registers (measured: -2.3 % on a rank's eighth of C3)
+#endif
 template <bool COUNT, bool BEAM, bool DEFER>
-__global__ void __launch_bounds__(RT_CTA_THREADS, RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
+__global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
                                                                                     unsigned int *counter, DirectState *state, HeavyQueue *hq,
                                                                                     float4 *hscratch, const RenderParams *gp) {
     const uint32_t lane = threadIdx.x & 31;
