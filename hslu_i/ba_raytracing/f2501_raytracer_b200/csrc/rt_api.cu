@@ -222,6 +222,20 @@ static int select_device(int device) {
     return RT_OK;
 }
 
+// global-memory copy of the kernel parameters for the out-of-line device paths (uploaded only when it changed)
+static int upload_params(rt_scene *s, const RenderParams &p, cudaStream_t stream) {
+    constexpr uint32_t RING = 16;  // pinned staging ring: a copy must outlive its async upload
+    if (!s->d_params) CU_CHECK(cudaMalloc((void **)&s->d_params, sizeof(RenderParams)));
+    if (!s->h_params) CU_CHECK(cudaMallocHost((void **)&s->h_params, RING * sizeof(RenderParams)));
+    if (s->d_params_valid && memcmp(&s->d_params_host, &p, sizeof(RenderParams)) == 0) return RT_OK;
+    RenderParams *stage = s->h_params + (s->h_params_next++ % RING);
+    memcpy(stage, &p, sizeof(RenderParams));
+    CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
+    memcpy(&s->d_params_host, &p, sizeof(RenderParams));
+    s->d_params_valid = true;
+    return RT_OK;
+}
+
 // enqueue render + resolve on `stream`; slab outputs are device pointers
 static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, uint32_t *d_argb, uint8_t *d_mask, cudaStream_t stream,
                           uint64_t *launches) {
@@ -292,11 +306,18 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     if (bounces) {
         // per-sample reflection / refraction trees: persistent megakernel
         CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
+        // shadow beams (lanes lighting their own hit) need M copies per light and usable bounds of the cloud points
+        const RenderParams *gp = nullptr;
+        if (p.M > 1 && p.LM > 0 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(p.cloud_lo[0] + p.cloud_lo[1] + p.cloud_lo[2]) &&
+            std::isfinite(p.cloud_hi[0] + p.cloud_hi[1] + p.cloud_hi[2])) {
+            if ((rc = upload_params(s, p, stream))) return rc;
+            gp = s->d_params;
+        }
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
         if (count)
-            render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
+            render_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p, gp);
         else
-            render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
+            render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p, gp);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
@@ -357,16 +378,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter
             hq = s->heavy_queue;
             s->frame_has_watchdog = true;
-            constexpr uint32_t RING = 16;
-            if (!s->d_params) CU_CHECK(cudaMalloc((void **)&s->d_params, sizeof(RenderParams)));
-            if (!s->h_params) CU_CHECK(cudaMallocHost((void **)&s->h_params, RING * sizeof(RenderParams)));
-            if (!s->d_params_valid || memcmp(&s->d_params_host, &pd, sizeof(RenderParams)) != 0) {  // steady state: nothing to upload
-                RenderParams *stage = s->h_params + (s->h_params_next++ % RING);
-                *stage = pd;
-                CU_CHECK(cudaMemcpyAsync(s->d_params, stage, sizeof(RenderParams), cudaMemcpyHostToDevice, stream));
-                s->d_params_host = pd;
-                s->d_params_valid = true;
-            }
+            if ((rc = upload_params(s, pd, stream))) return rc;
         }
         unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
         if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));

@@ -190,8 +190,52 @@ struct WarpShared {
     uint32_t cloud[32][MAX_SM_LIGHTS];
 };
 
+struct LightSums {  // running diffuse / specular light sums of one sample
+    float3 d, s;
+};
+// All L x M light copies for ONE shading point, in the reference's light order, with one shadow beam per
+// light (rt_device.cuh): what a lane of render_kernel runs for its own hit when most lanes of the warp have
+// one.  Out of line, parameters from their global-memory copy: render_kernel is register-starved as it is.
+constexpr uint32_t BEAM_MIN_LIVE = 12;  // below: the (hit, copy) pairs are spread over all 32 lanes instead
 template <bool COUNT>
-__global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel(const RenderParams p) {
+__device__ __noinline__ LightSums beam_lighting(const RenderParams *gp, float3 P, float3 N, float3 view, float3 mcolor, float mshininess,
+                                                uint32_t cloud_x, uint32_t pix_y, Counters *cn_out) {
+    const RenderParams &p = *gp;
+    const DScene &sc = p.sc;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    Counters cn = {0, 0, 0, 0, 0, 0};
+    LightSums out;
+    out.d = out.s = splat(0.0f);
+    const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
+    const float3 clo = f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s, chi = f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
+    const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
+    uint32_t cand[BEAM_MAX_CAND];
+    for (uint32_t li = 0; li < sc.n_lights; li++) {
+        const LightCopy L = load_light(p, li);
+        const uint32_t cloud = cloud_index(p.seed, cloud_x, pix_y, li, p.K);
+        const float3 lmin = L.pos + clo, lmax = L.pos + chi;  // the copies' `lpos + rp * w2s` is monotonic in rp
+        const Beam beam = make_beam(P, lmin, lmax, pad);
+        const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
+        const int n_cand = beam_collect<COUNT>(sc, beam, P, C - P, hh, cand, cn);
+        int32_t last_occluder = -1;
+        for (uint32_t c = 0; c < p.M; c++) {
+            float3 dc, spc;
+            shade_pair<COUNT, 1>(p, P, N, view, mcolor, mshininess, copy_position(p, L.pos, cloud, c), L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
+                                 &last_occluder);
+            out.d = out.d + dc;
+            out.s = out.s + spc;
+        }
+    }
+    if (COUNT && cn_out) {
+        cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
+        cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
+    }
+    return out;
+}
+
+// gp: global-memory copy of `p` when shadow beams may be used (M > 1, usable cloud bounds), else NULL
+template <bool COUNT>
+__global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel(const RenderParams p, const RenderParams *gp) {
     __shared__ WarpShared smem[CTA_WARPS];
     WarpShared &ws = smem[threadIdx.x >> 5];
     const uint32_t lane = threadIdx.x & 31;
@@ -321,7 +365,19 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
         // lane s < n_live accumulates the light sums of hit slot s (in light order, like the
         // reference's `for light in lights`); when all 32 lanes are live, slot == lane == owner.
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
+        // most lanes have a hit and the lights have M > 1 copies: every lane lights its OWN hit, one shadow beam
+        // per light (2.5x fewer instructions per ray than a BVH walk per copy; same sums in the same order)
+        const bool lane_beams = gp != nullptr && n_live >= BEAM_MIN_LIVE;
+        if (lane_beams) {
+            if (hit) {
+                const float4 ma = __ldg(sc.mats + 3 * (h.meta & rtb::PRIM_MATERIAL_MASK)), mb = __ldg(sc.mats + 3 * (h.meta & rtb::PRIM_MATERIAL_MASK) + 1);
+                const LightSums ls = beam_lighting<COUNT>(gp, P, N, d, f3(ma.x, ma.y, ma.z), mb.x, packet_noaa ? pix_x / 8u : pix_x, pix_y, COUNT ? &cn : nullptr);
+                sum_d = ls.d;
+                sum_s = ls.s;
+            }
+        }
         __syncwarp();
+        if (!lane_beams) {
         if (p.M > 1) {  // SceneLightSource::preprocess: one cloud per (pixel, light) (light.rs:183-225)
             for (uint32_t i = lane; i < n_live * MAX_SM_LIGHTS; i += 32) {
                 uint32_t s = i / MAX_SM_LIGHTS, li = i % MAX_SM_LIGHTS;
@@ -382,6 +438,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
             sum_d = f3(__shfl_sync(FULL, sum_d.x, src), __shfl_sync(FULL, sum_d.y, src), __shfl_sync(FULL, sum_d.z, src));
             sum_s = f3(__shfl_sync(FULL, sum_s.x, src), __shfl_sync(FULL, sum_s.y, src), __shfl_sync(FULL, sum_s.z, src));
         }
+        }  // !lane_beams
 
         // ---------------------------------------------------------------- combine + spawn (owner lane)
         if (hit) {
@@ -462,6 +519,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
         atomicAdd(p.counters + 2, cn.box);
         atomicAdd(p.counters + 3, cn.tri);
         atomicAdd(p.counters + 4, cn.sph);
+        atomicAdd(p.counters + 5, cn.beam_prim);
     }
 }
 
@@ -597,9 +655,6 @@ RT_DEV SampleRec rebuild_sample(const RenderParams &p, uint32_t item) {
     return r;
 }
 
-struct LightSums {  // running diffuse / specular light sums of one sample
-    float3 d, s;
-};
 // single_raytrace without bounces (raytracer_renderer.rs:195-257): the last light group publishes the sample
 RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float3 sum_d, float3 sum_s) {
     const float3 ambient = (r.mcolor * splat(1.0f)) * 0.08f;

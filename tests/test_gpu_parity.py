@@ -363,3 +363,21 @@ def test_place_tiles_and_kernel_times(pkg, scenes):
     assert np.array_equal(mask.cpu().numpy(), host.hit_mask)
     times = dev.kernel_times(world)
     assert len(times) == world and (times > 0).all()
+
+
+@pytest.mark.parametrize("scene_name,features,kw", [
+    ("main", "default,simd_render", dict(width=285, height=238, n_light_clouds=256)),
+    ("semesterbild", "extreme_quality,realistic,simd_render", dict(width=144, height=120, n_light_clouds=128)),
+])
+def test_bounce_kernel_beams_equal_per_ray_traversal(pkg, scenes, scene_name, features, kw):
+    """render_kernel (reflection / refraction trees): lanes that light their own hit with one shadow beam per
+    light give the image of the all-lanes (hit, copy) scheme with per-ray traversal bit for bit."""
+    L = pkg._lib
+    flat, dev = scenes(scene_name, features)
+    beam, _ = dev.render(pkg.RenderConfig.from_features(features, 8, **kw))
+    ray, _ = dev.render(pkg.RenderConfig.from_features(features, 8, extra_flags=L.FLAG_PER_RAY_SHADOWS, **kw))
+    assert np.array_equal(beam.buffer, ray.buffer) and np.array_equal(beam.hit_mask, ray.hit_mask)
+    _, sb = dev.render(pkg.RenderConfig.from_features(features, 8, extra_flags=L.FLAG_COUNT_WORK, **kw))
+    _, sr = dev.render(pkg.RenderConfig.from_features(features, 8, extra_flags=L.FLAG_COUNT_WORK | L.FLAG_PER_RAY_SHADOWS, **kw))
+    assert (sb["closest_rays"], sb["shadow_rays"]) == (sr["closest_rays"], sr["shadow_rays"])
+    assert sr["beam_triangle_tests"] == 0 and sb["beam_triangle_tests"] > 0 and sb["box_tests"] < sr["box_tests"]
