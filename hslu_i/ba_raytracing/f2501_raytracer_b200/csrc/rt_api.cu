@@ -67,10 +67,8 @@ struct rt_scene {
     unsigned int *work_counter = nullptr;
     unsigned long long *counters = nullptr;
     uint32_t *slab_argb = nullptr;
-    uint8_t *slab_mask = nullptr;
-    size_t slab_cap = 0, slab_mask_cap = 0;
+    size_t slab_cap = 0;
     uint32_t *pinned_argb = nullptr;
-    uint8_t *pinned_mask = nullptr;
     size_t pinned_cap = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -241,43 +239,6 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
                           uint64_t *launches) {
     fill_params(s, cfg, p);
     s->frame_has_watchdog = false;
-    if (p.LM > 0 && p.M > 1) {
-        const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
-        const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
-                            cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && cfg->width == s->clouds_w && cfg->height == s->clouds_h &&
-                            s->clouds;
-        if (!cached) {
-            int rc = grow(s->clouds_raw, s->clouds_raw_cap, n_pts * 3 * sizeof(float));
-            if (rc) return rc;
-            if ((rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4)))) return rc;
-            CU_CHECK(cudaMemcpyAsync(s->clouds_raw, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
-            scale_clouds_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, stream>>>(s->clouds_raw, s->clouds, (uint32_t)n_pts, p.w2s_w, p.w2s_h, p.w2s_d);
-            CU_CHECK(cudaGetLastError());
-            if (launches) *launches += 1;
-            for (int k = 0; k < 3; k++) {
-                float lo = INFINITY, hi = -INFINITY;
-                for (size_t i = 0; i < n_pts; i++) {
-                    const float v = cfg->light_clouds[3 * i + k];
-                    if (!std::isfinite(v)) lo = -INFINITY, hi = INFINITY;  // no usable bound: beams are switched off
-                    lo = std::min(lo, v);
-                    hi = std::max(hi, v);
-                }
-                s->cloud_lo[k] = lo;
-                s->cloud_hi[k] = hi;
-            }
-            s->clouds_epoch = cfg->tables_epoch;
-            s->clouds_src = cfg->light_clouds;
-            s->clouds_k = cfg->n_light_clouds;
-            s->clouds_m = p.M;
-            s->clouds_w = cfg->width;
-            s->clouds_h = cfg->height;
-        }
-        p.clouds = s->clouds;
-        for (int k = 0; k < 3; k++) {
-            p.cloud_lo[k] = s->cloud_lo[k];
-            p.cloud_hi[k] = s->cloud_hi[k];
-        }
-    }
     size_t n_samples = (size_t)p.local_rows * p.width * p.S;
     int rc = grow(s->samples, s->samples_cap, std::max<size_t>(n_samples, 1) * sizeof(float4));
     if (rc) return rc;
@@ -303,6 +264,49 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         primary_kernel<false><<<pgrid, 128, 0, stream>>>(p);
     CU_CHECK(cudaGetLastError());
     if (launches) *launches += 1;
+    // the soft-shadow cloud table is needed from here on: its host-side work (bounds scan, staging of the
+    // host-to-device copy) overlaps the primary pre-pass kernel that is already running
+    if (p.LM > 0 && p.M > 1) {
+        const size_t n_pts = (size_t)cfg->n_light_clouds * p.M;
+        const bool cached = cfg->tables_epoch != 0 && cfg->tables_epoch == s->clouds_epoch && cfg->light_clouds == s->clouds_src &&
+                            cfg->n_light_clouds == s->clouds_k && p.M == s->clouds_m && cfg->width == s->clouds_w && cfg->height == s->clouds_h &&
+                            s->clouds;
+        if (!cached) {
+            rc = grow(s->clouds_raw, s->clouds_raw_cap, n_pts * 3 * sizeof(float));
+            if (rc) return rc;
+            if ((rc = grow(s->clouds, s->clouds_cap, n_pts * sizeof(float4)))) return rc;
+            CU_CHECK(cudaMemcpyAsync(s->clouds_raw, cfg->light_clouds, n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+            scale_clouds_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, stream>>>(s->clouds_raw, s->clouds, (uint32_t)n_pts, p.w2s_w, p.w2s_h, p.w2s_d);
+            CU_CHECK(cudaGetLastError());
+            if (launches) *launches += 1;
+            {  // bounds of the points (one pass; a non-finite point leaves no usable bound: beams are switched off)
+                float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                bool finite = true;
+                const float *pt = cfg->light_clouds;
+                for (size_t i = 0; i < n_pts; i++, pt += 3) {
+                    lo[0] = std::min(lo[0], pt[0]); hi[0] = std::max(hi[0], pt[0]);
+                    lo[1] = std::min(lo[1], pt[1]); hi[1] = std::max(hi[1], pt[1]);
+                    lo[2] = std::min(lo[2], pt[2]); hi[2] = std::max(hi[2], pt[2]);
+                    finite &= (pt[0] - pt[0] == 0.0f) & (pt[1] - pt[1] == 0.0f) & (pt[2] - pt[2] == 0.0f);
+                }
+                for (int k = 0; k < 3; k++) {
+                    s->cloud_lo[k] = finite ? lo[k] : -INFINITY;
+                    s->cloud_hi[k] = finite ? hi[k] : INFINITY;
+                }
+            }
+            s->clouds_epoch = cfg->tables_epoch;
+            s->clouds_src = cfg->light_clouds;
+            s->clouds_k = cfg->n_light_clouds;
+            s->clouds_m = p.M;
+            s->clouds_w = cfg->width;
+            s->clouds_h = cfg->height;
+        }
+        p.clouds = s->clouds;
+        for (int k = 0; k < 3; k++) {
+            p.cloud_lo[k] = s->cloud_lo[k];
+            p.cloud_hi[k] = s->cloud_hi[k];
+        }
+    }
     if (bounces) {
         // per-sample reflection / refraction trees: persistent megakernel
         CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
@@ -553,13 +557,12 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->slab_mask};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->h_params) cudaFreeHost(s->h_params);
     if (s->h_watchdog) cudaFreeHost(s->h_watchdog);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
-    if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -613,43 +616,38 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
     const uint32_t rows = local_rows_of(cfg);
     const size_t n_pix = (size_t)rows * cfg->width;
     if ((rc = grow(s->slab_argb, s->slab_cap, std::max<size_t>(n_pix, 1) * sizeof(uint32_t)))) return rc;
-    if ((rc = grow(s->slab_mask, s->slab_mask_cap, std::max<size_t>(n_pix, 1)))) return rc;
     if (s->pinned_cap < n_pix) {
         if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
-        if (s->pinned_mask) cudaFreeHost(s->pinned_mask);
         s->pinned_argb = nullptr;
-        s->pinned_mask = nullptr;
         s->pinned_cap = 0;
         CU_CHECK(cudaMallocHost((void **)&s->pinned_argb, std::max<size_t>(n_pix, 1) * sizeof(uint32_t)));
-        CU_CHECK(cudaMallocHost((void **)&s->pinned_mask, std::max<size_t>(n_pix, 1)));
         s->pinned_cap = n_pix;
     }
     RenderParams p;
     uint64_t launches = 0;
     CU_CHECK(cudaEventRecord(s->ev0, s->stream));
-    rc = enqueue_render(s, cfg, p, s->slab_argb, s->slab_mask, s->stream, &launches);
+    rc = enqueue_render(s, cfg, p, s->slab_argb, nullptr, s->stream, &launches);  // (the hit mask is slab != 0)
     if (rc) return rc;
     CU_CHECK(cudaEventRecord(s->ev1, s->stream));
-    if (n_pix) {
-        CU_CHECK(cudaMemcpyAsync(s->pinned_argb, s->slab_argb, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-        CU_CHECK(cudaMemcpyAsync(s->pinned_mask, s->slab_mask, n_pix, cudaMemcpyDeviceToHost, s->stream));
-    }
+    if (n_pix) CU_CHECK(cudaMemcpyAsync(s->pinned_argb, s->slab_argb, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     if ((rc = enqueue_watchdog_fetch(s, s->stream))) return rc;
     CU_CHECK(cudaStreamSynchronize(s->stream));
     if ((rc = check_watchdog(s))) return rc;
-    // ImageBuffer semantics (reference src/renderer/mod.rs:116-125): only hit pixels are stored
+    // ImageBuffer semantics (reference src/renderer/mod.rs:116-125): only hit pixels are stored.  A slab pixel is
+    // 0xFFrrggbb for a hit and 0 for a miss (resolve_kernel), so the hit mask is `pixel != 0`: no second copy.
     const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
     for (uint32_t lr = 0; lr < rows; lr++) {
         const size_t row = image_row_of(cfg, lr);
         const uint32_t *src = s->pinned_argb + (size_t)lr * cfg->width;
-        const uint8_t *msk = s->pinned_mask + (size_t)lr * cfg->width;
         uint32_t *dst = out_argb + row * cfg->width;
-        uint8_t *dmask = out_hit_mask ? out_hit_mask + row * cfg->width : nullptr;
-        for (uint32_t x = 0; x < cfg->width; x++) {
-            if (msk[x]) dst[x] = src[x];
-            else if (zero_misses) dst[x] = 0;
+        if (zero_misses)
+            memcpy(dst, src, (size_t)cfg->width * sizeof(uint32_t));
+        else
+            for (uint32_t x = 0; x < cfg->width; x++) dst[x] = src[x] ? src[x] : dst[x];
+        if (out_hit_mask) {
+            uint8_t *dmask = out_hit_mask + row * cfg->width;
+            for (uint32_t x = 0; x < cfg->width; x++) dmask[x] = src[x] != 0u;
         }
-        if (dmask) memcpy(dmask, msk, cfg->width);
     }
     if (stats) {
         memset(stats, 0, sizeof(*stats));
