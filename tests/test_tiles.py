@@ -30,6 +30,21 @@ def test_tiles_partition_the_rows(pkg, height, tile_rows, world):
     assert tile_rows_of_rank(rc, tile_rows, 0, 1) == list(range(height))
 
 
+@pytest.mark.parametrize("height,tile_rows,world", [(640, 2, 8), (950, 4, 8), (23, 3, 2), (5, 8, 4), (641, 1, 3)])
+def test_place_tiles_mapping_inverts_the_tile_bookkeeping(pkg, height, tile_rows, world):
+    """place_tiles_kernel (rt_kernels.cuh) maps image row -> (rank, local row) with
+    t = row / tile_rows, rank = t % world, local = (t / world) * tile_rows + row % tile_rows;
+    that must be the inverse of rt_tile_row(), which every rank uses to place its rows."""
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import tile_rows_of_rank
+
+    rc = pkg.RenderConfig.from_features("", 0, height=height)
+    owned = [tile_rows_of_rank(rc, tile_rows, r, world) for r in range(world)]
+    for row in range(height):
+        t, r_in = divmod(row, tile_rows)
+        rank, local = t % world, (t // world) * tile_rows + r_in
+        assert owned[rank][local] == row
+
+
 def test_invalid_tiling_is_rejected(lib, pkg):
     rc = pkg.RenderConfig.from_features("", 0).with_tiles(4, 5, 2)  # rank >= world
     # validation happens before any device work
