@@ -101,6 +101,7 @@ def _declare(lib: C.CDLL) -> None:
         "rt_tile_row": (u32, [P(Config), u32]),
         "rt_scatter_tile_rows": (i32, [P(Config), vp, vp, u32, vp]),
         "rt_place_tiles": (i32, [P(Config), vp, u64, vp, vp, vp]),
+        "rt_bvh_digest": (i32, [P(SceneDesc), P(u64), P(u32), P(u32)]),
         "rt_trace_closest": (i32, [vp, u32, vp, u32, vp, vp]),
         "rt_trace_shadow": (i32, [vp, u32, vp, vp, u32, vp]),
         "rt_sampler_aa_table": (i32, [u64, u32, i32, vp, u32]),

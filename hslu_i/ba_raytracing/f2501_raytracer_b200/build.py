@@ -28,7 +28,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2",
-    "-shared", "-cudart", "static",
+    "-shared", "-cudart", "static", "-lpthread",
 ]
 
 

@@ -7,7 +7,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <queue>
+#include <thread>
 
 #include "rt_internal.h"
 
@@ -52,13 +56,36 @@ struct Builder {
     bool median_only = false;
     float c_isect = 1.25f;
     uint32_t max_leaf = MAX_LEAF;
+    // what build() works on: the arrays above, or (a subtree built by a worker thread) its parent's
+    const Box *pb = nullptr;
+    const float *ce = nullptr;
+    uint32_t *ord = nullptr;
+    // parallel build: subtrees of at most `task_size` references (0 = off) are set aside as tasks while the
+    // top of the tree is built, then built by worker threads and spliced in.  A subtree depends only on its
+    // range of `order`, so the tree is the one the sequential recursion builds.
+    uint32_t task_size = 0;
+    struct Task {
+        uint32_t first, count;
+        int depth;
+        int32_t parent;
+        bool left;
+    };
+    std::vector<Task> tasks;
+
+    int32_t child(uint32_t first, uint32_t count, int depth, int32_t parent, bool left) {
+        if (task_size && count <= task_size && count >= 1024) {
+            tasks.push_back({first, count, depth, parent, left});
+            return -2;  // patched by build_parallel
+        }
+        return build(first, count, depth);
+    }
 
     int32_t build(uint32_t first, uint32_t count, int depth) {
         Node2 nd;
         Box cb;
         for (uint32_t i = first; i < first + count; i++) {
-            nd.box.grow(pbox[order[i]]);
-            cb.grow_pt(&centroid[3 * order[i]]);
+            nd.box.grow(pb[ord[i]]);
+            cb.grow_pt(&ce[3 * ord[i]]);
         }
         int32_t idx = (int32_t)nodes.size();
         nodes.push_back(nd);
@@ -82,10 +109,10 @@ struct Builder {
                 uint32_t bc[NB] = {0};
                 float scale = (float)NB / ext;
                 for (uint32_t i = first; i < first + count; i++) {
-                    uint32_t p = order[i];
-                    int b = std::min(NB - 1, std::max(0, (int)((centroid[3 * p + a] - lo) * scale)));
+                    uint32_t p = ord[i];
+                    int b = std::min(NB - 1, std::max(0, (int)((ce[3 * p + a] - lo) * scale)));
                     bc[b]++;
-                    bb[b].grow(pbox[p]);
+                    bb[b].grow(pb[p]);
                 }
                 float rarea[NB];
                 uint32_t rcnt[NB];
@@ -115,11 +142,11 @@ struct Builder {
                 if (count <= max_leaf && best >= C_ISECT * (float)count) return make_leaf();
                 float lo = cb.lo[axis], scale = (float)NB / (cb.hi[axis] - cb.lo[axis]);
                 uint32_t split_bin = mid;
-                auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
-                    int b = std::min(NB - 1, std::max(0, (int)((centroid[3 * p + axis] - lo) * scale)));
+                uint32_t *it = std::partition(ord + first, ord + first + count, [&](uint32_t p) {
+                    int b = std::min(NB - 1, std::max(0, (int)((ce[3 * p + axis] - lo) * scale)));
                     return (uint32_t)b < split_bin;
                 });
-                mid = (uint32_t)(it - order.begin());
+                mid = (uint32_t)(it - ord);
                 if (mid == first || mid == first + count) axis = -1;
             }
         }
@@ -130,14 +157,58 @@ struct Builder {
             for (int k = 1; k < 3; k++)
                 if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
             mid = first + count / 2;
-            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
-                             [&](uint32_t x, uint32_t y) { return centroid[3 * x + a] < centroid[3 * y + a]; });
+            std::nth_element(ord + first, ord + mid, ord + first + count, [&](uint32_t x, uint32_t y) { return ce[3 * x + a] < ce[3 * y + a]; });
         }
-        int32_t l = build(first, mid - first, depth + 1);
-        int32_t r = build(mid, first + count - mid, depth + 1);
+        int32_t l = child(first, mid - first, depth + 1, idx, true);
+        int32_t r = child(mid, first + count - mid, depth + 1, idx, false);
         nodes[idx].left = l;
         nodes[idx].right = r;
         return idx;
+    }
+
+    // root of the tree over all of `order`, built with `threads` threads
+    int32_t build_parallel(uint32_t n, unsigned threads) {
+        pb = pbox.data();
+        ce = centroid.data();
+        ord = order.data();
+        tasks.clear();
+        task_size = (threads > 1 && n >= 65536) ? std::max<uint32_t>(n / (4 * threads), 2048) : 0;
+        const int32_t root = build(0, n, 0);
+        if (tasks.empty()) return root;
+        std::vector<std::vector<Node2>> sub(tasks.size());
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= tasks.size()) return;
+                Builder w;
+                w.median_only = median_only;
+                w.c_isect = c_isect;
+                w.max_leaf = max_leaf;
+                w.pb = pb;
+                w.ce = ce;
+                w.ord = ord;
+                w.nodes.reserve(2 * (size_t)tasks[i].count);
+                w.build(tasks[i].first, tasks[i].count, tasks[i].depth);
+                sub[i] = std::move(w.nodes);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < threads; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        for (size_t i = 0; i < tasks.size(); i++) {  // splice: the subtree's root is its node 0
+            const int32_t offset = (int32_t)nodes.size();
+            for (Node2 nd : sub[i]) {
+                if (nd.count == 0) {
+                    nd.left += offset;
+                    nd.right += offset;
+                }
+                nodes.push_back(nd);
+            }
+            (tasks[i].left ? nodes[tasks[i].parent].left : nodes[tasks[i].parent].right) = offset;
+        }
+        return root;
     }
 };
 
@@ -163,6 +234,14 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     for (uint32_t i = 0; i < nt; i++)
         if (d->triangles[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u: material index out of range", i);
 
+    const bool verbose = getenv("RT_BVH_VERBOSE") != nullptr;  // stage timings on stderr (tuning)
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char *name) {
+        if (!verbose) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rt_bvh] %-28s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     out = FlatScene();
     out.n_mats = d->n_materials;
     out.n_lights = d->n_lights;
@@ -202,6 +281,8 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     if (const char *e = getenv("RT_BVH_MAX_LEAF")) b.max_leaf = std::min<uint32_t>(MAX_LEAF, std::max(1, atoi(e)));
     float split_div = 0.0f;
     if (const char *e = getenv("RT_BVH_SPLIT_DIV")) split_div = (float)atof(e);
+    unsigned build_threads = std::max(1u, std::thread::hardware_concurrency());
+    if (const char *e = getenv("RT_BVH_THREADS")) build_threads = (unsigned)std::max(1, atoi(e));
     Box exact_scene;
     float max_abs = 1.0f;
     for (uint32_t i = 0; i < ns; i++) {
@@ -306,6 +387,7 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
             }
         }
     }
+    stage("primitive boxes");
     const uint32_t n_refs = (uint32_t)ref_prim.size();
     out.n_prims = n_refs;  // slots = references
     Box scene;
@@ -327,7 +409,8 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
         for (uint32_t i = 0; i < n_refs; i++) b.order[i] = i;
         b.nodes.clear();
         b.nodes.reserve(2 * (size_t)n_refs + 1);
-        int32_t root = n_refs ? b.build(0, n_refs, 0) : -1;
+        int32_t root = n_refs ? b.build_parallel(n_refs, build_threads) : -1;
+        stage("BVH2 build");
 
         out.nodes.clear();
         out.max_depth = 0;
@@ -398,6 +481,7 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
             }
         }
         out.n_nodes = (uint32_t)(out.nodes.size() / 32);
+        stage("collapse to BVH4");
         if (out.max_depth <= MAX_BVH4_DEPTH) break;
         if (attempt == 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "BVH depth %u exceeds the traversal stack", out.max_depth);
     }
@@ -448,7 +532,32 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
             }
         }
     }
+    stage("primitive records");
     return RT_OK;
 }
 
 }  // namespace rtb
+
+// Debug / parity entry point (include/rt_api.h): host-only build + digest of the flattened arrays.
+extern "C" int rt_bvh_digest(const rt_scene_desc *desc, uint64_t *out_digest, uint32_t *out_nodes, uint32_t *out_depth) {
+    if (!out_digest) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_bvh_digest: null output");
+    rtb::FlatScene flat;
+    int rc = rtb::build_flat_scene(desc, flat);
+    if (rc) return rc;
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over nodes, primitive records and stored normals
+    auto mix = [&](const std::vector<float> &v) {
+        const unsigned char *p = (const unsigned char *)v.data();
+        for (size_t i = 0, n = v.size() * sizeof(float); i < n; i++) {
+            h ^= p[i];
+            h *= 1099511628211ull;
+        }
+    };
+    mix(flat.nodes);
+    mix(flat.prims);
+    mix(flat.shade_n);
+    *out_digest = h;
+    if (out_nodes) *out_nodes = flat.n_nodes;
+    if (out_depth) *out_depth = flat.max_depth;
+    return RT_OK;
+}
+

@@ -214,6 +214,12 @@ int rt_trace_closest(rt_scene *scene, uint32_t flags, const float *rays, uint32_
 int rt_trace_shadow(rt_scene *scene, uint32_t flags, const float *rays, const float *max_dist,
                     uint32_t n, float *out);
 
+/* Debug/parity: builds the BVH of `desc` on the host only (no device needed) and returns an FNV-1a digest
+ * of the flattened node / primitive / normal arrays, the BVH4 node count and depth.  The build is
+ * multi-threaded (all host threads; RT_BVH_THREADS overrides) and the result must not depend on the
+ * thread count. */
+int rt_bvh_digest(const rt_scene_desc *desc, uint64_t *out_digest, uint32_t *out_nodes, uint32_t *out_depth);
+
 /* ---- samplers (stand-ins for fast_poisson 1.0.2, seeded; host code) -------------------------- */
 
 /* ANTIALIASING_SAMPLES table: [0,0], 8 x [1,1], then (randomness != 0) the first table_len-1

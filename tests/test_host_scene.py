@@ -159,3 +159,23 @@ def test_camera_projection_of_scene_corners(pkg):
     # back-wall top-left corner ~ (35, 68) and top-right ~ (688, 103) in output.png
     assert np.abs(px - np.array([34.5, 67])).sum(1).min() < 6
     assert np.abs(px - np.array([687.5, 104])).sum(1).min() < 6
+
+
+def test_parallel_bvh_build_is_independent_of_the_thread_count(pkg, lib, monkeypatch):
+    """rt_scene_create builds the BVH with all host threads (subtrees set aside as tasks, spliced back in);
+    the flattened node / primitive arrays must be those of the sequential build, bit for bit."""
+    import ctypes as C
+
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+    def digest(flat, threads):
+        monkeypatch.setenv("RT_BVH_THREADS", str(threads))
+        d = flat.desc()
+        h, n, depth = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        pkg._lib.check(lib.rt_bvh_digest(C.byref(d), C.byref(h), C.byref(n), C.byref(depth)))
+        return h.value, n.value, depth.value
+
+    for flat in (pkg.example_scene("semesterbild", "high_quality").flatten(), large_mesh_scene("high_quality", nx=256, ny=256).flatten()):
+        ref = digest(flat, 1)
+        assert ref[1] > 0 and 0 < ref[2] <= 20
+        assert digest(flat, 2) == ref and digest(flat, 7) == ref
