@@ -75,6 +75,9 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+BAND_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32)  # rt_band_callback
+
+
 class RtError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"librt_b200 error {code}: {message}")
@@ -95,6 +98,7 @@ def _declare(lib: C.CDLL) -> None:
         "rt_scene_create": (i32, [P(SceneDesc), i32, P(vp)]),
         "rt_scene_destroy": (None, [vp]),
         "rt_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),
+        "rt_render_progressive": (i32, [vp, P(Config), vp, vp, u32, vp, vp, P(Stats)]),
         "rt_render_device": (i32, [vp, P(Config), vp, vp, vp, P(Stats)]),
         "rt_kernel_times": (i32, [vp, u32, vp, P(u32)]),
         "rt_tile_local_rows": (u32, [P(Config)]),

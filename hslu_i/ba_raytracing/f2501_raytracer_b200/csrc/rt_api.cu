@@ -664,6 +664,42 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
     return RT_OK;
 }
 
+int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, uint32_t band_rows, rt_band_callback on_band,
+                          void *user, rt_stats *stats) {
+    if (!s || !out_argb || band_rows == 0) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: null scene / output or band_rows == 0");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (cfg->tile_world > 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: cfg must not use row tiles");
+    // a band = one row tile: tile b of `n_bands` tiles of band_rows rows, owned by "rank" b
+    const uint32_t n_bands = (cfg->height + band_rows - 1) / band_rows;
+    rt_stats total;
+    memset(&total, 0, sizeof(total));
+    for (uint32_t b = 0; b < n_bands; b++) {
+        rt_config band = *cfg;
+        band.tile_rows = band_rows;
+        band.tile_rank = b;
+        band.tile_world = n_bands;
+        rt_stats st;
+        if ((rc = rt_render(s, &band, out_argb, out_hit_mask, &st))) return rc;
+        total.kernel_ms += st.kernel_ms;
+        total.total_ms += st.total_ms;
+        total.closest_rays += st.closest_rays;
+        total.shadow_rays += st.shadow_rays;
+        total.box_tests += st.box_tests;
+        total.triangle_tests += st.triangle_tests;
+        total.sphere_tests += st.sphere_tests;
+        total.kernel_launches += st.kernel_launches;
+        total.beam_triangle_tests += st.beam_triangle_tests;
+        total.prepass_box_tests += st.prepass_box_tests;
+        total.prepass_triangle_tests += st.prepass_triangle_tests;
+        total.prepass_sphere_tests += st.prepass_sphere_tests;
+        const uint32_t first = b * band_rows, n_rows = std::min(band_rows, cfg->height - first);
+        if (on_band && on_band(user, first, n_rows)) break;
+    }
+    if (stats) *stats = total;
+    return RT_OK;
+}
+
 int rt_kernel_times(rt_scene *s, uint32_t n, float *out_ms, uint32_t *out_n) {
     if (!s || !out_ms || !out_n) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_kernel_times: null argument");
     CU_CHECK(cudaSetDevice(s->device));

@@ -124,6 +124,15 @@ class DeviceScene:
         L.check(self._lib.rt_render(self._h, C.byref(rc.cfg), L.ptr(buf.buffer), L.ptr(buf.hit_mask), C.byref(st)))
         return buf, st.as_dict()
 
+    def render_progressive(self, rc: RenderConfig, buffer: ImageBuffer | None = None, band_rows: int = 64, on_band=None) -> tuple[ImageBuffer, dict]:
+        """rt_render_progressive: the frame fills in band by band; `on_band(first_row, n_rows)` is called after
+        each band is in `buffer` (return True to stop), like the reference's window watching the render thread."""
+        buf = buffer or ImageBuffer(rc.cfg.width, rc.cfg.height)
+        st = L.Stats()
+        cb = L.BAND_CALLBACK(lambda _user, first, n: 1 if (on_band and on_band(first, n)) else 0)
+        L.check(self._lib.rt_render_progressive(self._h, C.byref(rc.cfg), L.ptr(buf.buffer), L.ptr(buf.hit_mask), band_rows, cb, None, C.byref(st)))
+        return buf, st.as_dict()
+
     def render_device(self, rc: RenderConfig, d_argb: int, d_mask: int | None, stream: int | None = None,
                       want_stats: bool = False) -> dict | None:
         """rt_render_device: outputs are device pointers (e.g. torch tensors' data_ptr())."""

@@ -178,6 +178,16 @@ void rt_scene_destroy(rt_scene *scene);
 int rt_render(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask,
               rt_stats *stats);
 
+/* Progressive variant of rt_render: the frame is rendered in horizontal bands of `band_rows` rows, top to
+ * bottom; after each band has been merged into `out_argb` / `out_hit_mask`, `on_band(user, first_row, n_rows)`
+ * is called (may be NULL) -- the reference's window shows the image filling in while the render thread works
+ * (src/output/window.rs:73-84, src/main.rs:342-347).  A non-zero return value of the callback stops the render
+ * (rt_render_progressive then returns RT_OK; the remaining rows are untouched).  `cfg` must not use row tiles.
+ * The image is exactly rt_render's.  `stats` (optional) sums the bands. */
+typedef int (*rt_band_callback)(void *user, uint32_t first_row, uint32_t n_rows);
+int rt_render_progressive(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask,
+                          uint32_t band_rows, rt_band_callback on_band, void *user, rt_stats *stats);
+
 /* Same, but the outputs are DEVICE pointers and the work is enqueued on `cuda_stream`
  * (a cudaStream_t; NULL is the legacy default stream).  With row tiles the output is the rank's COMPACT slab:
  * local row j holds image row rt_tile_row(cfg, j).  The call returns after enqueueing unless

@@ -408,3 +408,27 @@ def test_gpu_frame_vs_reference_render_dense_grid(pkg, scenes):
     d = np.abs(got[ref_mask] - ref[ref_mask]).max(-1)
     assert (d == 0).mean() >= 0.55 and (d <= 1).mean() >= 0.85 and (d <= 5).mean() >= 0.95 and (d <= 20).mean() >= 0.99
     assert np.abs(got[ref_mask] - ref[ref_mask]).mean() <= 1.0
+
+
+def test_progressive_render_fills_in_band_by_band(pkg, scenes):
+    """rt_render_progressive: same image as rt_render, the callback sees every band once, top to bottom,
+    with the band's rows already in the host buffer; a callback returning non-zero stops the render."""
+    feat = "anti_aliasing,soft_shadows,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 1, width=256, height=214, n_light_clouds=64)
+    full, _ = dev.render(rc)
+    seen = []
+    buf = pkg.ImageBuffer(256, 214)
+
+    def on_band(first, n):
+        rows = buf.hit_mask.reshape(214, 256)
+        assert np.array_equal(rows[first:first + n], full.hit_mask.reshape(214, 256)[first:first + n])
+        assert not rows[first + n:].any()
+        seen.append((first, n))
+
+    prog, st = dev.render_progressive(rc, buf, band_rows=48, on_band=on_band)
+    assert seen == [(0, 48), (48, 48), (96, 48), (144, 48), (192, 22)]
+    assert np.array_equal(prog.buffer, full.buffer) and np.array_equal(prog.hit_mask, full.hit_mask)
+    assert st["kernel_launches"] >= 3 * 5
+    part, _ = dev.render_progressive(rc, None, band_rows=48, on_band=lambda first, n: first >= 48)
+    assert part.hit_mask.reshape(214, 256)[:96].any() and not part.hit_mask.reshape(214, 256)[96:].any()

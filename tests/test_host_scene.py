@@ -179,3 +179,17 @@ def test_parallel_bvh_build_is_independent_of_the_thread_count(pkg, lib, monkeyp
         ref = digest(flat, 1)
         assert ref[1] > 0 and 0 < ref[2] <= 20
         assert digest(flat, 2) == ref and digest(flat, 7) == ref
+
+
+def test_file_output_writes_the_framebuffer_as_rgb8_png(pkg, tmp_path):
+    """FileOutput::render_buffer (reference src/output/file.rs:27-49): RGB8 PNG of the u32 buffer, untouched pixels black."""
+    PIL = pytest.importorskip("PIL.Image")
+    buf = pkg.ImageBuffer(7, 5)
+    rng = np.random.default_rng(3)
+    buf.buffer[:] = rng.integers(0, 1 << 24, 35, dtype=np.uint32) | np.uint32(0xFF000000)
+    buf.buffer[::4] = 0  # untouched
+    out = tmp_path / "frame.png"
+    pkg.FileOutput(out).render_buffer(buf)
+    img = PIL.open(out)
+    assert img.mode == "RGB" and img.size == (7, 5)
+    assert np.array_equal(np.asarray(img), buf.rgb())
