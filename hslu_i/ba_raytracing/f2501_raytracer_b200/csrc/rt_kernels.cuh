@@ -131,18 +131,32 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const DScene &sc = p.sc;
     dc = splat(0.0f);
     spc = splat(0.0f);
+    // The shadow ray exactly as the reference builds it (light.rs:261-299, raytracer_renderer.rs:773-800):
+    //   ldir = normalize(lpos - hp), q = hp + ldir * eps_d, maxd = |lpos - q|, d = normalize(ldir) (Ray::new).
+    // Three IEEE square roots and two IEEE reciprocals per ray; in the normal range (always, short of a light
+    // sitting on the surface) they are taken without nvcc's per-call range checks (rt_device.cuh).
     const float3 l2p = lpos - hp;
-    const float3 ldir = normalized3(l2p);
-    const float3 q = hp + ldir * p.eps_d;
-    const float maxd = mag3(lpos - q);
+    const float d2 = dot3(l2p, l2p);
+    float3 ldir = l2p * rcp_rn_normal(sqrt_rn_normal(d2));
+    float3 q = hp + ldir * p.eps_d;
+    const float3 lq = lpos - q;
+    const float m2 = dot3(lq, lq);
+    float maxd = sqrt_rn_normal(m2);
+    float3 d = ldir * rcp_rn_normal(sqrt_rn_normal(dot3(ldir, ldir)));
+    if (!((d2 > 1e-30f) & (d2 < 1e30f) & (m2 > 1e-30f))) {  // outside the range of the sequences above, or NaN
+        ldir = normalized3(l2p);
+        q = hp + ldir * p.eps_d;
+        maxd = mag3(lpos - q);
+        d = normalized3(ldir);
+    }
     ShadowResult sh;
     if (MODE == 1)
-        sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, normalized3(ldir), maxd, cull, cn)
-                         : trace_shadow_outlined<COUNT>(sc, q, normalized3(ldir), maxd, cull, &cn);
+        sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, d, maxd, cull, cn)
+                         : trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
     else if (MODE == 2)
-        sh = trace_shadow_outlined<COUNT>(sc, q, normalized3(ldir), maxd, cull, &cn);
+        sh = trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
     else
-        sh = trace_shadow<COUNT>(sc, q, normalized3(ldir), maxd, cull, cn);
+        sh = trace_shadow<COUNT>(sc, q, d, maxd, cull, cn);
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
     const float diffuse = smax(dot3(hn, ldir), 0.0f);
