@@ -18,4 +18,4 @@ for tag, extra in (("beam", 0), ("ray", L.FLAG_PER_RAY_SHADOWS)):
     lib.rt_dbg_counters(out)
     dev.render(rc)
     lib.rt_dbg_counters(out)
-    print(tag, "pretest_reject", out[0], "t_reject", out[1], "uv_reject", out[2], "hit", out[3], flush=True)
+    print(tag, "t_reject", out[1], "uv_reject", out[2], "hit", out[3], flush=True)
