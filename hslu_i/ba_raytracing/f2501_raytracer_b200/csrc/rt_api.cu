@@ -377,6 +377,8 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         HeavyQueue *hq = nullptr;
         if (defer) {
             if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
+            pd.heavy_cap = HEAVY_CAP;
+            if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
             rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;
             CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter

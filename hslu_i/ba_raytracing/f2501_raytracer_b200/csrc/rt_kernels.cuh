@@ -49,6 +49,7 @@ struct RenderParams {
     uint32_t tile_rows, tile_rank, tile_world, local_rows;
     uint32_t tiles_x, n_items;
     uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
+    uint32_t heavy_cap;    // direct_kernel: deferred units per launch (<= HEAVY_CAP; beyond: processed in place)
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
     uint4 *primary_hits;           // n_items: closest hit of every primary sample (primary_kernel): bits t, slot, prim, meta
     unsigned int *work_counter;
@@ -604,7 +605,7 @@ RT_DEV unsigned long long dbg_globaltimer() {
 // one sub-task = one light copy for the 32 samples of a unit.  Contributions go to a scratch slab; the
 // warp that completes a unit's last sub-task adds them to the predecessor's sums in copy order, i.e.
 // in the reference's light order: the image is bit-identical to processing the unit in place.
-constexpr uint32_t HEAVY_CAP = 16384;             // deferred units per launch (beyond: processed in place)
+constexpr uint32_t HEAVY_CAP = 16384;             // most deferred units per launch (RenderParams::heavy_cap; beyond: processed in place)
 constexpr uint32_t CHAIN_DEFERRED = 0x80000000u;  // flag in a chain tag: the unit is on the heavy list
 struct HeavyQueue {
     unsigned int n_heavy;       // units on the list
@@ -706,7 +707,7 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                     break;
                 }
                 const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
-                const unsigned int n = min(ld_volatile_u32(&hq->n_heavy), HEAVY_CAP);
+                const unsigned int n = min(ld_volatile_u32(&hq->n_heavy), p.heavy_cap);
                 if (want < n) {
                     idx = want;
                     c = t - want * p.M;
@@ -903,7 +904,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 unsigned int idx = 0;
                 if (lane == 0) idx = atomicAdd(&hq->n_heavy, 1u);
                 idx = __shfl_sync(FULL, idx, 0);
-                if (idx < HEAVY_CAP) {
+                if (idx < p.heavy_cap) {
                     defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (frame_tag + group_index) | CHAIN_DEFERRED, !last && r.hit,
                                last && r.valid && !r.hit);
 #ifdef RT_DBG_TAIL

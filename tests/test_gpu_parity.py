@@ -334,6 +334,13 @@ def test_deferred_units_are_bit_identical(pkg, scenes, monkeypatch):
     monkeypatch.setenv("RT_DEFER_BELOW", "0")        # never
     b, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
     assert a.hit_mask.any() and np.array_equal(a.buffer, b.buffer) and np.array_equal(a.hit_mask, b.hit_mask)
+    # a heavy list that is full almost at once: units beyond it are processed in place, and units continuing a
+    # deferred unit's sums wait for phase B to finish it
+    monkeypatch.setenv("RT_DEFER_BELOW", "1000000")
+    for cap in ("5", "0"):
+        monkeypatch.setenv("RT_HEAVY_CAP", cap)
+        c, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+        assert np.array_equal(a.buffer, c.buffer) and np.array_equal(a.hit_mask, c.hit_mask)
 
 
 def test_place_tiles_and_kernel_times(pkg, scenes):
