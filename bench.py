@@ -148,6 +148,8 @@ def run_reference(args) -> None:
     rays, dt, n = oracle_sample(flat, rc, 2 * cores, cores)
     per_pixel = max(dt / max(n, 1), 1e-6)
     step_budget = max(2.0, 150.0 / (args.steps + args.warmup))
+    if os.environ.get("RT_BENCH_REF_STEP_S"):  # tests: a much smaller sample per step
+        step_budget = float(os.environ["RT_BENCH_REF_STEP_S"])
     n_step = int(max(2 * cores, min(rc.cfg.width * rc.cfg.height, step_budget / per_pixel)))
     for i in range(args.warmup):
         oracle_sample(flat, rc, n_step, cores, seed=100 + i)
