@@ -1,0 +1,147 @@
+"""The product's device-side traversal and shadow-beam code (csrc/rt_device.cuh), compiled unchanged for the
+HOST by tests/emu/device_emu.cpp, against the CPU oracle and against itself -- without a GPU:
+
+* BVH4 traversal (trace_closest / trace_shadow over the arrays rt_bvh.cpp flattens) == the oracle's linear scan;
+* a shadow beam's candidate list (make_beam + beam_collect + beam_filter + trace_shadow_list) gives every one of
+  the M copies the result of its own BVH walk, bit for bit, on the shipped scenes.
+
+Test infrastructure only: the emulation answers raw queries, it is not a CPU path of the product."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+EMU_DIR = ROOT / "tests" / "emu"
+CSRC = ROOT / "hslu_i" / "ba_raytracing" / "f2501_raytracer_b200" / "csrc"
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def emu():
+    lib_path = EMU_DIR / "libdevice_emu.so"
+    srcs = [EMU_DIR / "device_emu.cpp", CSRC / "rt_bvh.cpp", CSRC / "rt_error.cpp"]
+    deps = srcs + [CSRC / "rt_device.cuh", CSRC / "rt_bvh.h", ROOT / "include" / "rt_api.h"]
+    if not lib_path.exists() or lib_path.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        cuda_inc = next((p for p in (Path("/usr/local/cuda/include"),) if (p / "cuda_runtime.h").exists()), None)
+        if cuda_inc is None:
+            pytest.skip("CUDA headers not found")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-shared", "-pthread",
+                        f"-I{cuda_inc}", f"-I{ROOT / 'include'}", f"-I{CSRC}", *map(str, srcs), "-o", str(lib_path)], check=True)
+    lib = C.CDLL(str(lib_path))
+    vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
+    lib.emu_scene_create.restype = vp
+    lib.emu_scene_create.argtypes = [vp]
+    lib.emu_scene_destroy.argtypes = [vp]
+    lib.emu_trace_closest.argtypes = [vp, u32, vp, u32, vp, vp]
+    lib.emu_trace_shadow.argtypes = [vp, u32, vp, vp, u32, vp]
+    lib.emu_beam_shadows.restype = C.c_int
+    lib.emu_beam_shadows.argtypes = [vp, u32, vp, vp, vp, f32, vp, u32, vp, vp, vp]
+    return lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def random_rays(rng, n):
+    o = rng.uniform(-0.3, 1.3, (n, 3)).astype(F)
+    tgt = rng.uniform(0.0, 1.0, (n, 3)).astype(F)
+    return np.ascontiguousarray(np.concatenate([o, tgt - o], 1), F)
+
+
+@pytest.mark.parametrize("scene_name,features,n", [("test_scene", "backface_culling", 20000), ("main", "", 4000)])
+def test_device_traversal_code_equals_linear_scan(pkg, oracle_mod, emu, scene_name, features, n):
+    flat = pkg.example_scene(scene_name, features).flatten()
+    desc = flat.desc()
+    h = emu.emu_scene_create(C.addressof(desc))
+    assert h
+    try:
+        rng = np.random.default_rng(21)
+        rays = random_rays(rng, n)
+        md = rng.uniform(0.05, 2.5, n).astype(F)
+        for flags in (0, pkg._lib.FLAG_BACKFACE_CULLING):
+            t = np.zeros(n, F)
+            prim = np.zeros(n, np.uint32)
+            emu.emu_trace_closest(h, flags, ptr(rays), n, ptr(t), ptr(prim))
+            t_o, p_o = oracle_mod.trace_closest(desc, rays, flags, oracle_mod.BRUTE)
+            assert np.array_equal(prim, p_o) and np.array_equal(t.view(np.uint32), t_o.view(np.uint32))
+            sh = np.zeros((n, 5), F)
+            emu.emu_trace_shadow(h, flags, ptr(rays), ptr(md), n, ptr(sh))
+            s_o = oracle_mod.trace_shadow(desc, rays, md, flags, oracle_mod.BRUTE)
+            assert np.array_equal(sh[:, 0], s_o[:, 0])
+            free = s_o[:, 0] == 0
+            assert np.allclose(sh[free, 1:], s_o[free, 1:], rtol=0, atol=2e-6)  # traversal order vs scan order
+            assert (p_o != 0xFFFFFFFF).mean() > 0.3 and 0.05 < (~free).mean() < 0.95
+    finally:
+        emu.emu_scene_destroy(h)
+
+
+def shading_points(pkg, emu, h, rc, pixels):
+    """Primary hit points of pixel centres, as the kernels compute them (get_pixel_color: origin on z = 0)."""
+    W, H = rc.cfg.width, rc.cfg.height
+    sh = F(H) / F(W)
+    sd = (F(1) + sh) / F(2)
+    focus = np.array([0.5, sh / F(2), F(-1.9) * sd], F)
+    o = np.stack([(pixels % W).astype(F) * (F(1) / F(W)), (pixels // W).astype(F) * (sh / F(H)), np.zeros(len(pixels), F)], 1).astype(F)
+    rays = np.ascontiguousarray(np.concatenate([o, o - focus], 1), F)
+    t = np.zeros(len(pixels), F)
+    prim = np.zeros(len(pixels), np.uint32)
+    emu.emu_trace_closest(h, 0, ptr(rays), len(pixels), ptr(t), ptr(prim))
+    d = rays[:, 3:] / np.sqrt((rays[:, 3:] ** 2).sum(1, dtype=F))[:, None]
+    hit = prim != 0xFFFFFFFF
+    return (o[hit] + d[hit] * t[hit, None]).astype(F), pixels[hit]
+
+
+@pytest.mark.parametrize("scene_name,features,extra_pixels", [
+    ("semesterbild", "high_quality,simd_render", [190 * 768 + 226, 187 * 768 + 226, 243 * 768 + 706, 171 * 768 + 734, 8 * 768 + 666]),
+    ("test_scene", "simd_render,backface_culling,soft_shadows", []),
+])
+def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, features, extra_pixels):
+    flat = pkg.example_scene(scene_name, features).flatten()
+    rc = pkg.RenderConfig.from_features(features, 3, n_light_clouds=256)
+    M = rc.cfg.light_multiplicator
+    assert M > 1
+    W, H = rc.cfg.width, rc.cfg.height
+    desc = flat.desc()
+    h = emu.emu_scene_create(C.addressof(desc))
+    try:
+        rng = np.random.default_rng(5)
+        pixels = np.unique(np.concatenate([rng.choice(W * H, 1000, replace=False), np.array(extra_pixels, np.int64)])).astype(np.int64)
+        P, _ = shading_points(pkg, emu, h, rc, pixels)
+        assert len(P) > 600
+        sh = F(H) / F(W)
+        w2s = np.array([F(1) / F(W), sh / F(H), ((F(1) + sh) / F(2)) / F((W + H) // 2)], F)
+        eps_d = F(1.1920929e-7) * (F(100) * ((F(1) + sh + (F(1) + sh) / F(2)) / F(3)))
+        clouds = rc.light_clouds.astype(F)  # (K, M, 3)
+        lo, hi = clouds.reshape(-1, 3).min(0), clouds.reshape(-1, 3).max(0)
+        flags = rc.cfg.flags & pkg._lib.FLAG_BACKFACE_CULLING
+        totals = np.zeros(5, np.uint64)
+        overflow = occluded = rays = 0
+        for i, p in enumerate(P):
+            for li, light in enumerate(flat.lights):
+                lpos = np.asarray(light["position"], F)
+                lmin, lmax = (lpos + lo * w2s).astype(F), (lpos + hi * w2s).astype(F)
+                copies = np.ascontiguousarray((lpos + clouds[(i * 7 + li * 13) % len(clouds)] * w2s).astype(F))
+                assert (copies >= lmin).all() and (copies <= lmax).all()  # the bounds are exact in float arithmetic
+                out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+                pc = np.ascontiguousarray(p)
+                n_cand = emu.emu_beam_shadows(h, flags, ptr(pc), ptr(lmin), ptr(lmax), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
+                # an occluded query carries no other state (shade_pair returns at once; the last-occluder probe may
+                # decide it before any transmissive hit is accumulated); everything else must agree bit for bit
+                assert np.array_equal(out_list[:, 0], out_ray[:, 0]), (i, li, n_cand)
+                free = out_ray[:, 0] == 0
+                assert np.array_equal(out_list[free].view(np.uint32), out_ray[free].view(np.uint32)), (i, li, n_cand)
+                assert (out_list[~free, 1] == 0).all() and (out_ray[~free, 1] == 0).all()
+                overflow += n_cand < 0
+                occluded += int(out_ray[:, 0].sum())
+                rays += M
+                totals += counts
+        assert 0.05 < occluded / rays < 0.95
+        assert overflow < 0.05 * len(P) * len(flat.lights)
+        # the point of the exercise: one hull walk + a short list instead of M BVH walks
+        assert totals[0] < totals[3] / 5 and totals[2] + totals[1] < totals[4]
+    finally:
+        emu.emu_scene_destroy(h)
