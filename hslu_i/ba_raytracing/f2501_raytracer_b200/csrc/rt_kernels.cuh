@@ -231,7 +231,11 @@ __device__ __noinline__ LightSums beam_lighting(const RenderParams *gp, float3 P
         const float3 lmin = L.pos + clo, lmax = L.pos + chi;  // the copies' `lpos + rp * w2s` is monotonic in rp
         const Beam beam = make_beam(P, lmin, lmax, pad);
         const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
-        const int n_cand = beam_collect<COUNT>(sc, beam, P, C - P, hh, cand, cn);
+        const int n_cand = beam_collect<COUNT>(sc, beam, P, C - P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+        if (n_cand == BEAM_COVERED) {  // one opaque triangle occludes all M copies: M occluded queries, nothing to add
+            if (COUNT) cn.shadow += p.M;
+            continue;
+        }
         int32_t last_occluder = -1;
         for (uint32_t c = 0; c < p.M; c++) {
             float3 dc, spc;
@@ -893,8 +897,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
                 const Beam beam = make_beam(r.P, lmin, lmax, pad);
                 const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
-                n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn);
-                if (DEFER) defer = n_cand < 0;  // overflow: M separate BVH walks, everybody else in the warp waiting
+                n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+                if (DEFER) defer = n_cand == -1;  // overflow: M separate BVH walks, everybody else in the warp waiting
             }
         }
         if (DEFER && BEAM && deferring) {
@@ -938,8 +942,10 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             dbg_cur_info |= (unsigned long long)(mx & 0xFF);
         }
 #endif
-        // every lane shades its own sample against the group's light copies, in order
-        if (r.hit) {
+        // every lane shades its own sample against the group's light copies, in order (a beam that one opaque
+        // triangle occludes entirely is M occluded queries: nothing to trace, nothing to add)
+        if (COUNT && r.hit && n_cand == BEAM_COVERED) cn.shadow += n_in_group;
+        if (r.hit && n_cand != BEAM_COVERED) {
             for (uint32_t l = 0; l < n_in_group; l++) {
                 float3 dc, spc;
                 if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights

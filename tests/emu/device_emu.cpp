@@ -98,7 +98,8 @@ void emu_trace_shadow(void *h, uint32_t flags, const float *rays, const float *m
 // One shadow beam: shading point P, box [lmin, lmax] of the light copies, and the M copies themselves.  Builds the
 // beam as direct_kernel does, then answers every copy's shadow query twice: from the beam's candidate list
 // (trace_shadow_list, with the last-occluder probe carried along) and by its own BVH walk (trace_shadow).
-// Returns the number of candidates (-1: the list overflowed), the box / triangle / beam-triangle test counts.
+// Returns the number of candidates (-1: the list overflowed, -2 = BEAM_COVERED: one opaque triangle occludes every
+// ray of the beam -- out_list is then all "occluded"), the box / triangle / beam-triangle test counts.
 int emu_beam_shadows(void *h, uint32_t flags, const float *P3, const float *lmin3, const float *lmax3, float eps_d, const float *copies, uint32_t m,
                      float *out_list, float *out_ray, uint64_t *out_counts) {
     const DScene &sc = ((EmuScene *)h)->d;
@@ -109,7 +110,7 @@ int emu_beam_shadows(void *h, uint32_t flags, const float *P3, const float *lmin
     const Beam beam = make_beam(P, lmin, lmax, pad);
     const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
     uint32_t cand[BEAM_MAX_CAND];
-    const int n_cand = beam_collect<true>(sc, beam, P, C - P, hh, cand, cb);
+    const int n_cand = beam_collect<true>(sc, beam, P, C - P, hh, cand, cb, cull ? -1.0f : eps_d);  // (as direct_kernel calls it)
     int32_t last_occluder = -1;
     for (uint32_t c = 0; c < m; c++) {
         const float3 lpos = f3(copies[3 * c], copies[3 * c + 1], copies[3 * c + 2]);
@@ -118,7 +119,13 @@ int emu_beam_shadows(void *h, uint32_t flags, const float *P3, const float *lmin
         const float maxd = mag3(lpos - q);
         const float3 d = normalized3(ldir);
         put(out_ray + 5 * c, trace_shadow<true>(sc, q, d, maxd, cull, cr));
-        if (n_cand >= 0)
+        if (n_cand == BEAM_COVERED) {
+            ShadowResult occ;
+            occ.occluded = true;
+            occ.opacity = 0.0f;
+            occ.filter = splat(1.0f);
+            put(out_list + 5 * c, occ);
+        } else if (n_cand >= 0)
             put(out_list + 5 * c, trace_shadow_list<true>(sc, cand, n_cand, last_occluder, q, d, maxd, cull, cl));
         else
             put(out_list + 5 * c, trace_shadow<true>(sc, q, d, maxd, cull, cl));

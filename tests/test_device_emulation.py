@@ -119,7 +119,7 @@ def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, feature
         lo, hi = clouds.reshape(-1, 3).min(0), clouds.reshape(-1, 3).max(0)
         flags = rc.cfg.flags & pkg._lib.FLAG_BACKFACE_CULLING
         totals = np.zeros(5, np.uint64)
-        overflow = occluded = rays = 0
+        overflow = occluded = rays = covered = dark_beams = 0
         for i, p in enumerate(P):
             for li, light in enumerate(flat.lights):
                 lpos = np.asarray(light["position"], F)
@@ -135,12 +135,17 @@ def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, feature
                 free = out_ray[:, 0] == 0
                 assert np.array_equal(out_list[free].view(np.uint32), out_ray[free].view(np.uint32)), (i, li, n_cand)
                 assert (out_list[~free, 1] == 0).all() and (out_ray[~free, 1] == 0).all()
-                overflow += n_cand < 0
+                overflow += n_cand == -1
+                covered += n_cand == -2  # BEAM_COVERED: one opaque triangle occludes the whole beam (checked above: all occluded)
+                dark_beams += bool((out_ray[:, 0] == 1).all())
                 occluded += int(out_ray[:, 0].sum())
                 rays += M
                 totals += counts
         assert 0.05 < occluded / rays < 0.95
         assert overflow < 0.05 * len(P) * len(flat.lights)
+        print(f"\n{scene_name}: {len(P) * len(flat.lights)} beams, {dark_beams} fully occluded, {covered} of them decided by the cover test, {overflow} overflowed")
+        if not flags:
+            assert covered > 0
         # the point of the exercise: one hull walk + a short list instead of M BVH walks
         assert totals[0] < totals[3] / 5 and totals[2] + totals[1] < totals[4]
     finally:
