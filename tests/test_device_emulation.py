@@ -150,3 +150,66 @@ def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, feature
         assert totals[0] < totals[3] / 5 and totals[2] + totals[1] < totals[4]
     finally:
         emu.emu_scene_destroy(h)
+
+
+def test_cover_test_never_claims_a_beam_with_a_free_ray(pkg, emu):
+    """BEAM_COVERED (one opaque triangle / sphere occludes every ray of the beam, so none is traced) on random
+    single-primitive scenes with beams aimed at the primitive's silhouette: whenever the device code claims it,
+    every copy's own shadow query (trace_shadow, reference arithmetic) must be occluded."""
+    rng = np.random.default_rng(77)
+    mat = pkg.material([0.5, 0.5, 0.5])
+    eps_d = F(1.0927e-5)
+    M = 24
+    claimed = {"tri": 0, "sphere": 0, "sphere_inside": 0}
+    seen = {"tri": 0, "sphere": 0, "sphere_inside": 0}
+    for case in range(1500):
+        kind = ("tri", "sphere", "sphere_inside")[case % 3]
+        s = pkg.Scene()
+        if kind == "tri":
+            scale = 10 ** rng.uniform(-2.0, -0.2)
+            v1 = rng.uniform(0.2, 0.8, 3)
+            v2, v3 = v1 + rng.normal(0, scale, 3), v1 + rng.normal(0, scale, 3)
+            if np.linalg.norm(np.cross(v2 - v1, v3 - v1)) < 1e-10:
+                continue
+            s.add_triangle(v1.astype(F), v2.astype(F), v3.astype(F), mat)
+            u, v = rng.uniform(-0.2, 1.2, 2)
+            X = v1 + u * (v2 - v1) + v * (v3 - v1)  # aim: a point of the plane in / near the triangle
+            P = X + rng.normal(0, 1, 3) * 10 ** rng.uniform(-1.5, 0)
+            Cc = P + (X - P) * rng.uniform(1.02, 3.0)
+        else:
+            c = rng.uniform(0.3, 0.7, 3)
+            r = 10 ** rng.uniform(-1.7, -0.6)
+            s.add_sphere(c.astype(F), F(r), mat)
+            dirn = rng.normal(0, 1, 3)
+            dirn /= np.linalg.norm(dirn)
+            if kind == "sphere":
+                side = np.cross(dirn, rng.normal(0, 1, 3))
+                side /= np.linalg.norm(side)
+                X = c + side * r * rng.uniform(0, 1.2)  # aim inside / at / just outside the silhouette
+                P = X - dirn * r * rng.uniform(1.1, 15)
+                Cc = X + dirn * r * rng.uniform(0.3, 10)
+            else:  # the shading point ON the sphere, the light beyond it (or not)
+                P = c + dirn * np.float64(F(r))
+                away = rng.normal(0, 1, 3)
+                away /= np.linalg.norm(away)
+                Cc = P + away * r * rng.uniform(0.5, 10)
+        half = 10 ** rng.uniform(-3.3, -1.8, 3)
+        lmin, lmax = (Cc - half).astype(F), (Cc + half).astype(F)
+        copies = np.ascontiguousarray((lmin + rng.random((M, 3)).astype(F) * (lmax - lmin)).astype(F))
+        copies[:8] = [[(lmin, lmax)[(k >> a) & 1][a] for a in range(3)] for k in range(8)]
+        flat = s.flatten()
+        desc = flat.desc()
+        h = emu.emu_scene_create(C.addressof(desc))
+        try:
+            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+            pc = np.ascontiguousarray(P.astype(F))
+            n_cand = emu.emu_beam_shadows(h, 0, ptr(pc), ptr(lmin), ptr(lmax), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
+        finally:
+            emu.emu_scene_destroy(h)
+        seen[kind] += 1
+        if n_cand == -2:
+            claimed[kind] += 1
+            assert (out_ray[:, 0] == 1).all(), f"case {case} ({kind}): covered claimed but {int((out_ray[:, 0] == 0).sum())} copies are unoccluded"
+        else:
+            assert np.array_equal(out_list[:, 0], out_ray[:, 0])
+    assert all(claimed[k] > 20 for k in claimed), (claimed, seen)
