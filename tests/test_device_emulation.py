@@ -98,9 +98,16 @@ def shading_points(pkg, emu, h, rc, pixels):
 @pytest.mark.parametrize("scene_name,features,extra_pixels", [
     ("semesterbild", "high_quality,simd_render", [190 * 768 + 226, 187 * 768 + 226, 243 * 768 + 706, 171 * 768 + 734, 8 * 768 + 666]),
     ("test_scene", "simd_render,backface_culling,soft_shadows", []),
+    ("test_scene", "simd_render,soft_shadows", []),
+    ("large_mesh", "high_quality,simd_render", []),
 ])
 def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, features, extra_pixels):
-    flat = pkg.example_scene(scene_name, features).flatten()
+    if scene_name == "large_mesh":
+        from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+        flat = large_mesh_scene(features, nx=192, ny=192).flatten()
+    else:
+        flat = pkg.example_scene(scene_name, features).flatten()
     rc = pkg.RenderConfig.from_features(features, 3, n_light_clouds=256)
     M = rc.cfg.light_multiplicator
     assert M > 1
