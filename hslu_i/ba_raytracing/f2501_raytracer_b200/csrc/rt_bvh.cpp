@@ -72,6 +72,19 @@ struct Builder {
     };
     std::vector<Task> tasks;
 
+    unsigned wide_threads = 1;  // threads for the scans of big nodes (the sequential top of a parallel build)
+    template <typename Fn>
+    static void run_chunks(uint32_t first, uint32_t count, unsigned nthr, Fn fn) {
+        std::vector<std::thread> pool;
+        const uint32_t per = (count + nthr - 1) / nthr;
+        for (unsigned t = 1; t < nthr; t++) {
+            const uint32_t lo_i = first + std::min(count, t * per), hi_i = first + std::min(count, (t + 1) * per);
+            pool.emplace_back([=]() { fn(t, lo_i, hi_i); });
+        }
+        fn(0u, first, first + std::min(count, per));
+        for (auto &th : pool) th.join();
+    }
+
     int32_t child(uint32_t first, uint32_t count, int depth, int32_t parent, bool left) {
         if (task_size && count <= task_size && count >= 1024) {
             tasks.push_back({first, count, depth, parent, left});
@@ -83,9 +96,26 @@ struct Builder {
     int32_t build(uint32_t first, uint32_t count, int depth) {
         Node2 nd;
         Box cb;
-        for (uint32_t i = first; i < first + count; i++) {
-            nd.box.grow(pb[ord[i]]);
-            cb.grow_pt(&ce[3 * ord[i]]);
+        // big nodes (the top of a large tree) are scanned by all threads: min / max and counts merge exactly, so the
+        // result does not depend on how the range is cut
+        const unsigned nthr = (wide_threads > 1 && count >= 262144u) ? wide_threads : 1u;
+        if (nthr > 1) {
+            std::vector<Box> nb(nthr), cbs(nthr);
+            run_chunks(first, count, nthr, [&](unsigned t, uint32_t lo_i, uint32_t hi_i) {
+                for (uint32_t i = lo_i; i < hi_i; i++) {
+                    nb[t].grow(pb[ord[i]]);
+                    cbs[t].grow_pt(&ce[3 * ord[i]]);
+                }
+            });
+            for (unsigned t = 0; t < nthr; t++) {
+                nd.box.grow(nb[t]);
+                cb.grow(cbs[t]);
+            }
+        } else {
+            for (uint32_t i = first; i < first + count; i++) {
+                nd.box.grow(pb[ord[i]]);
+                cb.grow_pt(&ce[3 * ord[i]]);
+            }
         }
         int32_t idx = (int32_t)nodes.size();
         nodes.push_back(nd);
@@ -108,11 +138,29 @@ struct Builder {
                 Box bb[NB];
                 uint32_t bc[NB] = {0};
                 float scale = (float)NB / ext;
-                for (uint32_t i = first; i < first + count; i++) {
-                    uint32_t p = ord[i];
-                    int b = std::min(NB - 1, std::max(0, (int)((ce[3 * p + a] - lo) * scale)));
-                    bc[b]++;
-                    bb[b].grow(pb[p]);
+                if (nthr > 1) {
+                    std::vector<Box> tb((size_t)nthr * NB);
+                    std::vector<uint32_t> tc((size_t)nthr * NB, 0u);
+                    run_chunks(first, count, nthr, [&](unsigned t, uint32_t lo_i, uint32_t hi_i) {
+                        for (uint32_t i = lo_i; i < hi_i; i++) {
+                            uint32_t p = ord[i];
+                            int b = std::min(NB - 1, std::max(0, (int)((ce[3 * p + a] - lo) * scale)));
+                            tc[(size_t)t * NB + b]++;
+                            tb[(size_t)t * NB + b].grow(pb[p]);
+                        }
+                    });
+                    for (unsigned t = 0; t < nthr; t++)
+                        for (int b = 0; b < NB; b++) {
+                            bc[b] += tc[(size_t)t * NB + b];
+                            bb[b].grow(tb[(size_t)t * NB + b]);
+                        }
+                } else {
+                    for (uint32_t i = first; i < first + count; i++) {
+                        uint32_t p = ord[i];
+                        int b = std::min(NB - 1, std::max(0, (int)((ce[3 * p + a] - lo) * scale)));
+                        bc[b]++;
+                        bb[b].grow(pb[p]);
+                    }
                 }
                 float rarea[NB];
                 uint32_t rcnt[NB];
@@ -172,6 +220,7 @@ struct Builder {
         ce = centroid.data();
         ord = order.data();
         tasks.clear();
+        wide_threads = threads;
         task_size = (threads > 1 && n >= 65536) ? std::max<uint32_t>(n / (4 * threads), 2048) : 0;
         const int32_t root = build(0, n, 0);
         if (tasks.empty()) return root;
