@@ -330,7 +330,7 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     if (const char *e = getenv("RT_BVH_MAX_LEAF")) b.max_leaf = std::min<uint32_t>(MAX_LEAF, std::max(1, atoi(e)));
     float split_div = 0.0f;
     if (const char *e = getenv("RT_BVH_SPLIT_DIV")) split_div = (float)atof(e);
-    unsigned build_threads = std::max(1u, std::thread::hardware_concurrency());
+    unsigned build_threads = std::min(32u, std::max(1u, std::thread::hardware_concurrency()));  // (memory-bound beyond that)
     if (const char *e = getenv("RT_BVH_THREADS")) build_threads = (unsigned)std::max(1, atoi(e));
     Box exact_scene;
     float max_abs = 1.0f;
