@@ -1,6 +1,12 @@
 // rt_kernels.cuh -- the render kernels (sm_100a).
 //
-// render_kernel: persistent warps.  Every lane owns one primary sample at a time and walks that
+// primary_kernel: closest hit of every primary sample, one thread per sample.
+// direct_kernel (configs without bounces, the headline path): persistent warps fetch units = (32 neighbouring
+// samples, one light's M soft-shadow copies); each lane builds ONE shadow beam for its sample (rt_device.cuh:
+// hull walk -> candidate list -> triangle culling -> cover test) and shades the M copies in order, the running
+// sums chained from light to light through tagged records; very expensive units are deferred and finished by
+// all warps together (DEFER variant).
+// render_kernel (bounce configs): persistent warps.  Every lane owns one primary sample at a time and walks that
 // sample's reflection/refraction tree depth-first with a private path stack; lanes refill from a
 // global work counter (warp-aggregated atomicAdd) the moment their tree is finished, so the
 // divergent closest-hit phase always runs with as many live lanes as there is work.  The
@@ -8,7 +14,8 @@
 // raytracer_renderer.rs:773-870) -- is NOT done per lane: the live hit records of the warp are
 // compacted into shared memory and the (hit, light copy) pairs are flattened over all 32 lanes,
 // so the shadow traversal runs at full warp occupancy however few lanes still have a live path,
-// and neighbouring lanes trace near-identical rays (same origin, jittered copies of one light).
+// and neighbouring lanes trace near-identical rays (same origin, jittered copies of one light); when most
+// lanes have a hit, each lights its own hit through shadow beams instead (beam_lighting).
 // resolve_kernel: sums the samples of a pixel in the reference's order, encodes to 0xFFRRGGBB.
 #pragma once
 #include "rt_device.cuh"
