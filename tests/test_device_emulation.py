@@ -220,3 +220,37 @@ def test_cover_test_never_claims_a_beam_with_a_free_ray(pkg, emu):
         else:
             assert np.array_equal(out_list[:, 0], out_ray[:, 0])
     assert all(claimed[k] > 20 for k in claimed), (claimed, seen)
+
+
+def test_beam_degenerate_inputs_equal_per_ray_traversal(pkg, emu):
+    """Corners of the beam construction on the semesterbild scene: a degenerate light box (one point), a shading
+    point inside the light box (the hull widens both ways on every axis), axis-aligned beams, a NaN shading point."""
+    feat = "high_quality,simd_render"
+    flat = pkg.example_scene("semesterbild", feat).flatten()
+    desc = flat.desc()
+    h = emu.emu_scene_create(C.addressof(desc))
+    eps_d = F(1.0927e-5)
+    M = 8
+    rng = np.random.default_rng(12)
+    try:
+        cases = []
+        for _ in range(60):
+            P = rng.uniform(0.05, 0.95, 3).astype(F)
+            L = rng.uniform(0.05, 0.95, 3).astype(F)
+            cases.append((P, L, L))                                                   # all copies in one point
+            cases.append((P, (P - F(0.002)).astype(F), (P + F(0.003)).astype(F)))     # the point inside the light box
+            a = rng.integers(3)
+            L2 = P.copy()
+            L2[a] = F(rng.uniform(0.05, 0.95))
+            cases.append((P, L2, (L2 + F(0.003)).astype(F)))                          # beam along one axis
+        cases.append((np.array([np.nan, 0.5, 0.5], F), np.array([0.2, 0.2, 0.2], F), np.array([0.21, 0.21, 0.21], F)))
+        for P, lmin, lmax in cases:
+            copies = np.ascontiguousarray((lmin + rng.random((M, 3)).astype(F) * (lmax - lmin)).astype(F))
+            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+            pc, lo, hi = np.ascontiguousarray(P), np.ascontiguousarray(lmin), np.ascontiguousarray(lmax)
+            emu.emu_beam_shadows(h, 0, ptr(pc), ptr(lo), ptr(hi), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
+            assert np.array_equal(out_list[:, 0], out_ray[:, 0]), (P, lmin, lmax)
+            free = out_ray[:, 0] == 0
+            assert np.array_equal(out_list[free].view(np.uint32), out_ray[free].view(np.uint32))
+    finally:
+        emu.emu_scene_destroy(h)
