@@ -24,6 +24,9 @@ namespace rtd {
 
 // Occupancy sweep on B200 (profiles/README.md): the kernel is latency bound, 28 warps/SM at 72
 // registers (a few hundred bytes of spills) beats 16 warps/SM at 125 registers without spills by 13 %.
+#ifndef RT_EMPTY_LIST_SKIP
+#define RT_EMPTY_LIST_SKIP 0  // off until it has been through the GPU tests (see RT_SELF_CULL in rt_device.cuh)
+#endif
 #ifndef RT_CTA_THREADS
 #define RT_CTA_THREADS 128
 #endif
@@ -158,6 +161,16 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
         d = normalized3(ldir);
     }
     ShadowResult sh;
+#if RT_EMPTY_LIST_SKIP
+    // (next round) an empty candidate list: the query is "nothing on the segment" whatever the ray -- the whole
+    // warp skips the list walk when none of its lanes has a candidate
+    if (MODE == 1 && n_cand == 0 && *last_occluder < 0) {
+        if (COUNT) cn.shadow++;
+        sh.occluded = false;
+        sh.opacity = 1.0f;
+        sh.filter = splat(1.0f);
+    } else
+#endif
     if (MODE == 1)
         sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, d, maxd, cull, cn)
                          : trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);

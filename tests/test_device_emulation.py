@@ -19,9 +19,8 @@ CSRC = ROOT / "hslu_i" / "ba_raytracing" / "f2501_raytracer_b200" / "csrc"
 F = np.float32
 
 
-@pytest.fixture(scope="module")
-def emu():
-    lib_path = EMU_DIR / "libdevice_emu.so"
+def _build_emu(lib_name, defines=()):
+    lib_path = EMU_DIR / lib_name
     srcs = [EMU_DIR / "device_emu.cpp", CSRC / "rt_bvh.cpp", CSRC / "rt_error.cpp"]
     deps = srcs + [CSRC / "rt_device.cuh", CSRC / "rt_bvh.h", ROOT / "include" / "rt_api.h"]
     if not lib_path.exists() or lib_path.stat().st_mtime < max(p.stat().st_mtime for p in deps):
@@ -29,7 +28,7 @@ def emu():
         if cuda_inc is None:
             pytest.skip("CUDA headers not found")
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-march=x86-64-v3", "-shared", "-pthread",
-                        f"-I{cuda_inc}", f"-I{ROOT / 'include'}", f"-I{CSRC}", *map(str, srcs), "-o", str(lib_path)], check=True)
+                        *defines, f"-I{cuda_inc}", f"-I{ROOT / 'include'}", f"-I{CSRC}", *map(str, srcs), "-o", str(lib_path)], check=True)
     lib = C.CDLL(str(lib_path))
     vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
     lib.emu_scene_create.restype = vp
@@ -40,6 +39,15 @@ def emu():
     lib.emu_beam_shadows.restype = C.c_int
     lib.emu_beam_shadows.argtypes = [vp, u32, vp, vp, vp, f32, vp, u32, vp, vp, vp]
     return lib
+
+
+@pytest.fixture(scope="module", params=["product", "next"])
+def emu(request):
+    """"product": the device code as the product builds it.  "next": with the compile-time switches that are off in
+    the product until they have been through the GPU tests (RT_SPHERE_MISS_CULL, RT_SELF_CULL), so that they are ready to flip."""
+    if request.param == "product":
+        return _build_emu("libdevice_emu.so")
+    return _build_emu("libdevice_emu_next.so", ("-DRT_SPHERE_MISS_CULL=1", "-DRT_SELF_CULL=1"))
 
 
 def ptr(a):
