@@ -130,6 +130,9 @@ int emu_beam_shadows(void *h, uint32_t flags, const float *P3, const float *lmin
         else
             put(out_list + 5 * c, trace_shadow<true>(sc, q, d, maxd, cull, cl));
     }
+    if (out_counts && n_cand > 0) {  // (diagnostics) the first candidates' reference primitive indices
+        for (int i = 0; i < 3; i++) out_counts[5 + i] = i < n_cand ? __float_as_uint(__ldg(sc.prims + 4 * (size_t)cand[i] + 3).x) : 0xFFFFFFFFull;
+    }
     if (out_counts) {
         out_counts[0] = cb.box;        // beam: box tests of the one hull walk
         out_counts[1] = cb.beam_prim;  // beam: triangle culling tests

@@ -133,7 +133,7 @@ def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, feature
         clouds = rc.light_clouds.astype(F)  # (K, M, 3)
         lo, hi = clouds.reshape(-1, 3).min(0), clouds.reshape(-1, 3).max(0)
         flags = rc.cfg.flags & pkg._lib.FLAG_BACKFACE_CULLING
-        totals = np.zeros(5, np.uint64)
+        totals = np.zeros(8, np.uint64)
         overflow = occluded = rays = covered = dark_beams = 0
         for i, p in enumerate(P):
             for li, light in enumerate(flat.lights):
@@ -141,7 +141,7 @@ def test_shadow_beam_lists_equal_per_ray_traversal(pkg, emu, scene_name, feature
                 lmin, lmax = (lpos + lo * w2s).astype(F), (lpos + hi * w2s).astype(F)
                 copies = np.ascontiguousarray((lpos + clouds[(i * 7 + li * 13) % len(clouds)] * w2s).astype(F))
                 assert (copies >= lmin).all() and (copies <= lmax).all()  # the bounds are exact in float arithmetic
-                out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+                out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(8, np.uint64)
                 pc = np.ascontiguousarray(p)
                 n_cand = emu.emu_beam_shadows(h, flags, ptr(pc), ptr(lmin), ptr(lmax), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
                 # an occluded query carries no other state (shade_pair returns at once; the last-occluder probe may
@@ -216,7 +216,7 @@ def test_cover_test_never_claims_a_beam_with_a_free_ray(pkg, emu):
         desc = flat.desc()
         h = emu.emu_scene_create(C.addressof(desc))
         try:
-            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(8, np.uint64)
             pc = np.ascontiguousarray(P.astype(F))
             n_cand = emu.emu_beam_shadows(h, 0, ptr(pc), ptr(lmin), ptr(lmax), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
         finally:
@@ -254,7 +254,7 @@ def test_beam_degenerate_inputs_equal_per_ray_traversal(pkg, emu):
         cases.append((np.array([np.nan, 0.5, 0.5], F), np.array([0.2, 0.2, 0.2], F), np.array([0.21, 0.21, 0.21], F)))
         for P, lmin, lmax in cases:
             copies = np.ascontiguousarray((lmin + rng.random((M, 3)).astype(F) * (lmax - lmin)).astype(F))
-            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(5, np.uint64)
+            out_list, out_ray, counts = np.zeros((M, 5), F), np.zeros((M, 5), F), np.zeros(8, np.uint64)
             pc, lo, hi = np.ascontiguousarray(P), np.ascontiguousarray(lmin), np.ascontiguousarray(lmax)
             emu.emu_beam_shadows(h, 0, ptr(pc), ptr(lo), ptr(hi), eps_d, ptr(copies), M, ptr(out_list), ptr(out_ray), ptr(counts))
             assert np.array_equal(out_list[:, 0], out_ray[:, 0]), (P, lmin, lmax)
