@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Benchmark of the render path: rays/s and ms/frame of one frame of a reference scene.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--scenes c1,c2,c4,c5|none] [--impl ours|reference]
 
 A "step" is one frame of the workload: primary rays, BVH traversal, shadow/transmittance rays,
 bounces, AA accumulation and the ARGB framebuffer write.  Default workload = BASELINE.json's
@@ -9,6 +9,10 @@ target config: semesterbild `high_quality` + `simd_render` (768x640, 16 AA sampl
 19 soft-shadow copies).  With N > 1 (torchrun, one rank per GPU) the frame is split into
 interleaved row tiles and gathered on rank 0 over NCCL; the frame (total work) is fixed, so the
 scaling is "strong".  Rays per frame come from the counter build of the same kernels (untimed).
+
+The metric is quoted "per scene": after the headline workload the same run measures the other BASELINE
+configs (`--scenes`, default c1,c2,c4,c5) with fewer steps and reports them in the `scenes` table of the
+same JSON line (ms/frame, rays/s, dominant kernel, roofline fraction, scene-create time).
 
 `--impl reference` times the reference's CPU algorithm (the brute-force C++ oracle, all host
 threads; the Rust crate cannot be built in this image) on a bounded pixel sample of the same
@@ -42,6 +46,8 @@ WORKLOADS = {
     "c5": ("large_mesh", "extreme_quality,realistic,high_resolution,simd_render",
            "semesterbild objects + synthetic 4 194 304-triangle relief, extreme_quality+realistic 1620x1350 S=24 M=28 depth 21/21 (BASELINE configs[4])"),
 }
+# (steps, warmup) of the per-scene table entries: bounded so that the default run stays within minutes
+SCENE_STEPS = {"c1": (3, 1), "c2": (10, 3), "c4": (10, 3), "c5": (2, 1), "c3": (10, 3), "c3_scalar": (10, 3), "c1lite": (10, 3)}
 # canonical algorithmic costs
 F_BOX, F_TRI, F_SPH = 22, 45, 22
 B_BOX, B_TRI, B_SPH = 32, 52, 20
@@ -108,9 +114,17 @@ def build_workload(name: str, seed: int):
     return flat, rc, features, desc
 
 
+def workload_config(flat, rc, features: str, desc: str, seed: int) -> dict:
+    """Identity of the workload: the same dict in our arm and in the reference arm (no arm-specific keys)."""
+    return {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
+            "primitives": flat.n_primitives, "lights": len(flat.lights), "samples_per_pixel": rc.samples_per_pixel,
+            "light_copies": rc.cfg.light_multiplicator, "reflection_depth": rc.cfg.reflection_max_depth,
+            "refraction_depth": rc.cfg.refraction_max_depth, "seed": seed}
+
+
 def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
     """Brute-force oracle (the reference's linear scan, 8-ray AVX2 packets = its `simd_render` path
-    where the config is a packet config, scalar otherwise) on a random pixel sample; returns rays, seconds."""
+    where the config is a packet config, scalar otherwise) on a random pixel sample; returns rays, seconds, pixels."""
     from oracle import oracle
 
     W, H = rc.cfg.width, rc.cfg.height
@@ -123,19 +137,28 @@ def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
     return cnt["closest_rays"] + cnt["shadow_rays"], dt, len(pix)
 
 
+def size_sample(flat, rc, cores: int, budget_s: float) -> int:
+    """Pixels per sample for ~budget_s of CPU work: a short probe (one pixel per thread -- the oracle hands out
+    chunks of n/(8 threads) pixels, so every thread is busy even then), a second probe ten times larger when
+    the first one was over in a blink, then scaled to the budget.  Never below 4 pixels per thread."""
+    frame = rc.cfg.width * rc.cfg.height
+    n = min(frame, 2 * cores)
+    _, dt, n = oracle_sample(flat, rc, n, cores, seed=7)
+    if dt < 0.5 and n < frame:
+        n = min(frame, 16 * n)
+        _, dt, n = oracle_sample(flat, rc, n, cores, seed=8)
+    per_pixel = max(dt / max(n, 1), 1e-7)
+    return int(max(min(4 * cores, frame), min(frame, budget_s / per_pixel)))
+
+
 def cpu_baseline(flat, rc, budget_s: float = 15.0) -> dict:
     cores = os.cpu_count() or 1
-    rays, dt, n = oracle_sample(flat, rc, 4 * cores, cores)
-    per_pixel = max(dt / max(n, 1), 1e-6)
-    n2 = int(max(4 * cores, min(rc.cfg.width * rc.cfg.height, budget_s / per_pixel)))
-    rays, dt, n = oracle_sample(flat, rc, n2, cores)
-    if dt < budget_s / 3 and n < rc.cfg.width * rc.cfg.height:  # the probe over-estimated the per-pixel cost
-        n3 = int(min(rc.cfg.width * rc.cfg.height, n * budget_s / max(dt, 1e-3)))
-        rays, dt, n = oracle_sample(flat, rc, n3, cores)
+    n = size_sample(flat, rc, cores, budget_s)
+    rays, dt, n = oracle_sample(flat, rc, n, cores)
     return {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
             "sample": f"{n} random pixels of the workload ({rays} rays, {dt:.1f} s), brute-force C++ oracle, "
                       f"8-ray AVX2 packets (the reference's simd_render instantiation: linear scan over all {flat.n_primitives} "
-                      f"primitives per packet), {cores} threads"}
+                      f"primitives per packet), {cores} threads, pixel queue in chunks of {max(1, min(64, n // (8 * cores)))}"}
 
 
 def run_reference(args) -> None:
@@ -144,13 +167,11 @@ def run_reference(args) -> None:
         return
     flat, rc, features, desc = build_workload(args.workload, args.seed)
     cores = os.cpu_count() or 1
-    # size one step to ~ (120 s / (K + W)) of CPU work
-    rays, dt, n = oracle_sample(flat, rc, 2 * cores, cores)
-    per_pixel = max(dt / max(n, 1), 1e-6)
-    step_budget = max(2.0, 150.0 / (args.steps + args.warmup))
+    # one step = a bounded pixel sample: ~ (150 s / (K + W)) of CPU work on all host threads
+    step_budget = max(2.0, 150.0 / max(args.steps + args.warmup, 1))
     if os.environ.get("RT_BENCH_REF_STEP_S"):  # tests: a much smaller sample per step
         step_budget = float(os.environ["RT_BENCH_REF_STEP_S"])
-    n_step = int(max(2 * cores, min(rc.cfg.width * rc.cfg.height, step_budget / per_pixel)))
+    n_step = size_sample(flat, rc, cores, step_budget)
     for i in range(args.warmup):
         oracle_sample(flat, rc, n_step, cores, seed=100 + i)
     tot_rays, tot_t = 0, 0.0
@@ -160,17 +181,23 @@ def run_reference(args) -> None:
         tot_t += dt
     value = tot_rays / tot_t
     frame_pixels = rc.cfg.width * rc.cfg.height
+    chunk = max(1, min(64, n_step // (8 * cores)))
+    threads_busy = min(cores, -(-n_step // chunk))
     line = {
         "impl": "reference", "metric": "rays_per_second", "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
-                   "step": f"{n_step} random pixels of the frame per step ({n_step / frame_pixels:.5f} of a frame)"},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_step} random pixels per step, brute-force C++ oracle with 8-ray AVX2 packets (the reference's simd_render linear scan), {cores} threads; "
+        "config": workload_config(flat, rc, features, desc, args.seed),
+        "run": {"step": f"{n_step} random pixels of the frame per step ({n_step / frame_pixels:.5f} of a frame)", "threads": threads_busy,
+                "pixel_queue_chunk": chunk,
+                "native_note": "librt_b200.so is loaded by this arm for HOST code only (scene construction / flattening, seeded sampler tables); "
+                               "no kernel is launched, the timed work is oracle/liboracle_rt.so"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads_busy, "kind": "port",
+                         "sample": f"{n_step} random pixels per step, brute-force C++ oracle with 8-ray AVX2 packets (the reference's simd_render linear scan), "
+                                   f"{threads_busy} threads busy of {cores} host threads; "
                                    "the Rust reference itself cannot be built in this image (no cargo/rustc, crates not vendored)"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "ms_per_frame_extrapolated": 1e3 * (tot_t / args.steps) * frame_pixels / n_step,
+        "ms_per_frame_extrapolated": 1e3 * (tot_t / max(args.steps, 1)) * frame_pixels / n_step,
     }
     emit(line)
 
@@ -198,6 +225,172 @@ def emit(line: dict) -> None:
         os.write(_REAL_STDOUT, data)
 
 
+class Ctx:
+    """Process-wide state of our arm: torch, the process group, helpers."""
+
+    def __init__(self, args):
+        import torch
+
+        self.torch = torch
+        self.args = args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: librt_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        self.fp32_peak = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _reduce(self, x: float, op) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allmax(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX) if self.dist is not None else x
+
+    def allsum(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.SUM) if self.dist is not None else x
+
+
+def measure(ctx: Ctx, name: str, steps: int, warmup: int, headline: bool) -> dict:
+    """One workload on this process group: counter passes (untimed), K timed device-resident steps, the
+    end-to-end leg through the host API.  Every rank runs it; rank 0 uses the result."""
+    import ctypes as C
+
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import DeviceScene, ImageBuffer, RenderConfig
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import _lib as L
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import TiledRenderer
+
+    torch, args, rank, world = ctx.torch, ctx.args, ctx.rank, ctx.world
+    lib = L.load()
+    t0 = time.perf_counter()
+    flat, rc, features, desc = build_workload(name, args.seed)
+    host_scene_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    dev = DeviceScene(flat, device=ctx.local_rank)  # rt_scene_create: BVH build + upload
+    torch.cuda.synchronize()
+    scene_create_ms = ctx.allmax(1e3 * (time.perf_counter() - t0))
+    tiled = TiledRenderer(dev, rc, rank, world, args.tile_rows)
+
+    # ---- untimed: work counters of this rank's tiles (counter build of the same kernels)
+    def count_pass(extra_flags: int) -> dict:
+        rcc = RenderConfig(L.Config(), rc.aa_table, rc.light_clouds)
+        C.memmove(C.byref(rcc.cfg), C.byref(tiled.rc.cfg), C.sizeof(L.Config))
+        rcc.cfg.flags |= L.FLAG_COUNT_WORK | extra_flags
+        stc = dev.render_device(rcc, tiled.slab.data_ptr(), tiled.mask.data_ptr(), None, want_stats=True)
+        out = {k: ctx.allsum(float(stc[k])) for k in ("closest_rays", "shadow_rays", "box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests",
+                                                       "prepass_box_tests", "prepass_triangle_tests", "prepass_sphere_tests")}
+        out["kernel_launches"] = int(stc["kernel_launches"])
+        return out
+
+    counts = count_pass(0)  # what the timed kernels execute (shadow beams)
+    rays_per_frame = counts["closest_rays"] + counts["shadow_rays"]
+
+    def alg(c):  # tests of the dominant kernel alone: totals minus the primary pre-pass kernel's share
+        nb, nt, ns = c["box_tests"] - c["prepass_box_tests"], c["triangle_tests"] - c["prepass_triangle_tests"], c["sphere_tests"] - c["prepass_sphere_tests"]
+        fl = nb * F_BOX + nt * F_TRI + ns * F_SPH + c["beam_triangle_tests"] * F_BEAM_TRI
+        by = nb * B_BOX + (nt + c["beam_triangle_tests"]) * B_TRI + ns * B_SPH
+        return fl, by
+
+    flops_alg, bytes_alg = alg(counts)
+    counts_ray = flops_ray = None
+    if headline:  # the same frame with one BVH walk per shadow ray: the canonical per-ray test counts
+        counts_ray = count_pass(L.FLAG_PER_RAY_SHADOWS)
+        assert rays_per_frame == counts_ray["closest_rays"] + counts_ray["shadow_rays"]
+        flops_ray, _ = alg(counts_ray)
+    if ctx.fp32_peak is None:
+        peak = C.c_double(0.0)
+        L.check(lib.rt_measure_fp32_peak(ctx.local_rank, C.byref(peak)))
+        ctx.fp32_peak = peak.value
+
+    # ---- warm-up
+    for _ in range(warmup):
+        tiled.step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps; per-step CUDA events on the launching stream, L2 flushed between steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    sampler = ClockSampler(ctx.local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.barrier()
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for i in range(steps):
+        ctx.flush.zero_()
+        ev[i][0].record()
+        tiled.render_local()
+        ev[i][1].record()
+        tiled.gather()
+        ev[i][2].record()
+    torch.cuda.synchronize()
+    ctx.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    tiled.check()  # the frames' device watchdog words (a wait loop that gave up = invalid frame)
+    dom_ms = dev.kernel_times(min(steps, 64))  # dominant kernel alone, one CUDA-event pair per timed step
+    dom_ms_max = ctx.allmax(float(dom_ms.mean()) if len(dom_ms) else 0.0)
+    step_ms = ctx.allmax(sum(e[0].elapsed_time(e[2]) for e in ev))
+    kern_ms_max = ctx.allmax(sum(e[0].elapsed_time(e[1]) for e in ev))
+    ms_per_step = step_ms / steps
+
+    # ---- end to end through the public host API: host buffers, copies inside the timed region
+    h2d = (rc.light_clouds.nbytes if rc.light_clouds is not None else 0) + 4
+    if world == 1:
+        buf = ImageBuffer(rc.cfg.width, rc.cfg.height)
+        rc_e2e = rc.uncached()  # tables_epoch = 0: the sampler tables are copied host-to-device on every call
+        dev.render(rc_e2e, buf)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            dev.render(rc_e2e, buf)  # H2D sampler tables, kernels, D2H framebuffer + mask, host merge
+        e2e_s = time.perf_counter() - t0
+        d2h = rc.cfg.width * rc.cfg.height * 4  # the frame; the hit mask is derived from it (pixel != 0)
+    else:
+        host = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.int32).pin_memory() if rank == 0 else None
+        host_m = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.uint8).pin_memory() if rank == 0 else None
+        ctx.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tiled.rc = tiled.rc.uncached()  # sampler tables host-to-device on every step
+        for _ in range(steps):
+            tiled.step()
+            if rank == 0:
+                host.copy_(tiled.frame, non_blocking=True)
+                host_m.copy_(tiled.frame_mask, non_blocking=True)
+            torch.cuda.synchronize()
+            ctx.barrier()
+        e2e_s = ctx.allmax(time.perf_counter() - t0)
+        d2h = rc.cfg.width * rc.cfg.height * 5
+        tiled.check()
+    e2e_ms = 1e3 * e2e_s / steps
+
+    bounces = bool(rc.cfg.flags & (L.FLAG_REFLECTIONS | L.FLAG_REFRACTIONS))
+    dominant_kernel = dev.dominant_kernel_name() if hasattr(dev, "dominant_kernel_name") else ("render_kernel" if bounces else "direct_kernel")
+    res = dict(name=name, flat=flat, rc=rc, features=features, desc=desc, counts=counts, counts_ray=counts_ray, rays_per_frame=rays_per_frame,
+               flops_alg=flops_alg, bytes_alg=bytes_alg, flops_ray=flops_ray, kernel_ms=dom_ms_max, render_ms=kern_ms_max / steps,
+               ms_per_step=ms_per_step, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, clocks=clocks, wall=wall, scene_create_ms=scene_create_ms,
+               host_scene_s=host_scene_s, dominant_kernel=dominant_kernel, steps=steps, warmup=warmup,
+               launches_per_step=int(counts["kernel_launches"]) + (0 if world == 1 else 1), bvh=dev.bvh_info() if hasattr(dev, "bvh_info") else None)
+    dev.close()
+    del tiled
+    torch.cuda.empty_cache()
+    return res
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -205,6 +398,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scenes", default=os.environ.get("RT_BENCH_SCENES", "c1,c2,c4,c5"),
+                    help="other BASELINE configs measured after the headline workload (comma list, or 'none')")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--tile-rows", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -215,213 +410,91 @@ def main() -> None:
         run_reference(args)
         return
 
-    import torch
-
-    from hslu_i.ba_raytracing.f2501_raytracer_b200 import DeviceScene, RenderConfig
-    from hslu_i.ba_raytracing.f2501_raytracer_b200 import _lib as L
-    from hslu_i.ba_raytracing.f2501_raytracer_b200.distributed import TiledRenderer
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: librt_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def allmax(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    lib = L.load()
-    flat, rc, features, desc = build_workload(args.workload, args.seed)
-    dev = DeviceScene(flat, device=local_rank)
-    tiled = TiledRenderer(dev, rc, rank, world, args.tile_rows)
-
-    # ---- untimed: work counters of this rank's tiles (counter build of the same kernels)
-    import ctypes as C
-
-    def count_pass(extra_flags: int) -> dict:
-        rcc = RenderConfig(L.Config(), rc.aa_table, rc.light_clouds)
-        C.memmove(C.byref(rcc.cfg), C.byref(tiled.rc.cfg), C.sizeof(L.Config))
-        rcc.cfg.flags |= L.FLAG_COUNT_WORK | extra_flags
-        stc = dev.render_device(rcc, tiled.slab.data_ptr(), tiled.mask.data_ptr(), None, want_stats=True)
-        out = {k: allsum(float(stc[k])) for k in ("closest_rays", "shadow_rays", "box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests",
-                                                  "prepass_box_tests", "prepass_triangle_tests", "prepass_sphere_tests")}
-        out["kernel_launches"] = int(stc["kernel_launches"])
-        return out
-
-    counts = count_pass(0)                          # what the timed kernels execute (shadow beams)
-    counts_ray = count_pass(L.FLAG_PER_RAY_SHADOWS)  # the same frame with one BVH walk per shadow ray
-    st = counts
-    rays_per_frame = counts["closest_rays"] + counts["shadow_rays"]
-    assert rays_per_frame == counts_ray["closest_rays"] + counts_ray["shadow_rays"]
-
-    def alg(c):  # tests of the dominant kernel alone: totals minus the primary pre-pass kernel's share
-        nb, nt, ns = c["box_tests"] - c["prepass_box_tests"], c["triangle_tests"] - c["prepass_triangle_tests"], c["sphere_tests"] - c["prepass_sphere_tests"]
-        fl = nb * F_BOX + nt * F_TRI + ns * F_SPH + c["beam_triangle_tests"] * F_BEAM_TRI
-        by = nb * B_BOX + (nt + c["beam_triangle_tests"]) * B_TRI + ns * B_SPH
-        return fl, by
-
-    flops_alg, bytes_alg = alg(counts)
-    flops_ray, bytes_ray = alg(counts_ray)
-
-    fp32_peak = C.c_double(0.0)
-    L.check(lib.rt_measure_fp32_peak(local_rank, C.byref(fp32_peak)))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    # ---- warm-up
-    for _ in range(max(args.warmup, 1) if args.warmup else 0):
-        tiled.step()
-    torch.cuda.synchronize()
-
-    # ---- timed region: exactly K steps; per-step CUDA events on the launching stream, L2 flushed between steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    barrier()
-    torch.cuda.synchronize()
-    wall0 = time.perf_counter()
-    for i in range(args.steps):
-        flush.zero_()
-        ev[i][0].record()
-        tiled.render_local()
-        ev[i][1].record()
-        tiled.gather()
-        ev[i][2].record()
-    torch.cuda.synchronize()
-    barrier()
-    wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
-    dom_ms = dev.kernel_times(min(args.steps, 64))  # dominant kernel alone, one CUDA-event pair per timed step
-    dom_ms_max = allmax(float(dom_ms.mean()) if len(dom_ms) else 0.0)
-    step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
-    kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
-    step_ms = allmax(step_ms)
-    kern_ms_max = allmax(kern_ms)
-    ms_per_step = step_ms / args.steps
-
-    # ---- end to end through the public host API: host buffers, copies inside the timed region
-    from hslu_i.ba_raytracing.f2501_raytracer_b200 import ImageBuffer
-
-    h2d = (rc.light_clouds.nbytes if rc.light_clouds is not None else 0) + 4
-    if world == 1:
-        buf = ImageBuffer(rc.cfg.width, rc.cfg.height)
-        rc_e2e = rc.uncached()  # tables_epoch = 0: the sampler tables are copied host-to-device on every call
-        dev.render(rc_e2e, buf)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            dev.render(rc_e2e, buf)  # H2D sampler tables, kernels, D2H framebuffer + mask, host merge
-        e2e_s = time.perf_counter() - t0
-        d2h = rc.cfg.width * rc.cfg.height * 4  # the frame; the hit mask is derived from it (pixel != 0)
-    else:
-        host = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.int32).pin_memory() if rank == 0 else None
-        host_m = torch.empty(rc.cfg.width * rc.cfg.height, dtype=torch.uint8).pin_memory() if rank == 0 else None
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        tiled.rc = tiled.rc.uncached()  # sampler tables host-to-device on every step
-        for _ in range(args.steps):
-            tiled.step()
-            if rank == 0:
-                host.copy_(tiled.frame, non_blocking=True)
-                host_m.copy_(tiled.frame_mask, non_blocking=True)
-            torch.cuda.synchronize()
-            barrier()
-        e2e_s = allmax(time.perf_counter() - t0)
-        d2h = rc.cfg.width * rc.cfg.height * 5
-    e2e_ms = 1e3 * e2e_s / args.steps
+    ctx = Ctx(args)
+    rank, world = ctx.rank, ctx.world
+    m = measure(ctx, args.workload, args.steps, args.warmup, headline=True)
+    scenes = {}
+    for name in [s for s in args.scenes.split(",") if s and s != "none" and s != args.workload]:
+        if name not in WORKLOADS:
+            raise SystemExit(f"unknown scene {name}")
+        k, w = SCENE_STEPS.get(name, (5, 2))
+        s = measure(ctx, name, k, w, headline=False)
+        ach = s["flops_alg"] / world / (s["kernel_ms"] * 1e-3) / 1e12 if s["kernel_ms"] else None
+        scenes[name] = {
+            "workload": s["desc"], "ms_per_frame": s["ms_per_step"], "rays_per_s": s["rays_per_frame"] / (s["ms_per_step"] * 1e-3),
+            "rays_per_frame": int(s["rays_per_frame"]), "e2e_ms_per_frame": s["e2e_ms"], "e2e_rays_per_s": s["rays_per_frame"] / (s["e2e_ms"] * 1e-3),
+            "steps": k, "warmup": w, "dominant_kernel": s["dominant_kernel"], "kernel_ms": s["kernel_ms"],
+            "roofline_frac_fp32": ach / ctx.fp32_peak if ach and ctx.fp32_peak else None, "achieved_tflops": ach,
+            "algorithmic_gbs": s["bytes_alg"] / world / (s["kernel_ms"] * 1e-3) / 1e9 if s["kernel_ms"] else None,
+            "scene_create_ms": s["scene_create_ms"], "primitives": s["flat"].n_primitives, "bvh": s["bvh"],
+            "tests_per_ray": {k2: s["counts"][k2] / s["rays_per_frame"] for k2 in ("box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests")},
+        }
 
     if rank == 0:
+        flat, rc, counts, counts_ray = m["flat"], m["rc"], m["counts"], m["counts_ray"]
+        rays_per_frame, kernel_ms = m["rays_per_frame"], m["kernel_ms"]
         peaks = {}
         try:
             peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except (OSError, ValueError):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        kernel_ms = dom_ms_max                    # the dominant kernel's own launch duration (max over ranks of the per-rank mean)
-        render_ms = kern_ms_max / args.steps      # primary + dominant + resolve kernels
-        bounces = bool(rc.cfg.flags & (L.FLAG_REFLECTIONS | L.FLAG_REFRACTIONS))
-        if bounces:
-            dominant_kernel = "render_kernel<false>"
-        elif rc.cfg.light_multiplicator > 1:
-            # rt_api.cu picks the DEFER variant for launches with < 100 units per resident warp
-            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            units = -(-tiled.rows * rc.cfg.width * rc.samples_per_pixel // 32) * len(flat.lights)
-            dominant_kernel = f"direct_kernel<false,true,{'true' if units // (sms * 7 * 4) < 100 else 'false'}>"
-        else:
-            dominant_kernel = "direct_kernel<false,false,false>"
+        fp32_peak = ctx.fp32_peak
         traffic, traffic_src = None, None
         try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this workload
             tj = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(args.workload)
-            if tj and tj.get("kernel") == dominant_kernel and world == 1:
+            if tj and tj.get("kernel", "").split("<")[0] == m["dominant_kernel"].split("<")[0] and world == 1:
                 traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         except (OSError, ValueError):
             pass
-        ach_tflops = flops_alg / world / (kernel_ms * 1e-3) / 1e12  # per GPU, dominant kernel
+        ach_tflops = m["flops_alg"] / world / (kernel_ms * 1e-3) / 1e12  # per GPU, dominant kernel
         line = {
-            "metric": "rays_per_second", "value": rays_per_frame / (ms_per_step * 1e-3), "unit": "rays/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "metric": "rays_per_second", "value": rays_per_frame / (m["ms_per_step"] * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "features": features, "width": rc.cfg.width, "height": rc.cfg.height,
-                       "primitives": flat.n_primitives, "lights": len(flat.lights), "samples_per_pixel": rc.samples_per_pixel,
-                       "light_copies": rc.cfg.light_multiplicator, "rays_per_frame": int(rays_per_frame),
-                       "closest_rays": int(counts["closest_rays"]), "shadow_rays": int(counts["shadow_rays"]),
-                       "parallelism": f"row tiles of {args.tile_rows} rows interleaved over {world} GPU(s), NCCL gather to rank 0",
-                       "l2": "flushed between timed steps (256 MiB write)", "seed": args.seed},
-            "ms_per_frame": ms_per_step,
-            "e2e": {"value": rays_per_frame / (e2e_ms * 1e-3), "unit": "rays/s", "ms_per_frame": e2e_ms,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(args.steps * (int(st["kernel_launches"]) + (0 if world == 1 else 1))),
+            "config": workload_config(flat, rc, m["features"], m["desc"], args.seed),
+            "run": {"parallelism": f"row tiles of {args.tile_rows} rows interleaved over {world} GPU(s), NCCL gather to rank 0",
+                    "l2": "flushed between timed steps (256 MiB write)", "rays_per_frame": int(rays_per_frame),
+                    "closest_rays": int(counts["closest_rays"]), "shadow_rays": int(counts["shadow_rays"])},
+            "ms_per_frame": m["ms_per_step"],
+            "e2e": {"value": rays_per_frame / (m["e2e_ms"] * 1e-3), "unit": "rays/s", "ms_per_frame": m["e2e_ms"],
+                    "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
+                    "scene_create_ms": m["scene_create_ms"],
+                    "ms_per_frame_with_scene_create": m["e2e_ms"] + m["scene_create_ms"],
+                    "note": "the Rust shim's render() flattens the scene and calls rt_scene_create on every call "
+                            "(reference times exactly that call, src/main.rs:331-334): scene_create_ms = host BVH build + upload, once per scene"},
+            "scene_create_ms": m["scene_create_ms"],
+            "gpu_launches": int(args.steps * m["launches_per_step"]),
             "executed_tests_per_ray": {k: counts[k] / rays_per_frame for k in ("box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests")},
-            "clocks": clocks,
-            "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak.value, "unit": "TFLOP/s",
-                         "frac": ach_tflops / fp32_peak.value if fp32_peak.value else None, "traffic": traffic,
-                         "kernel": dominant_kernel, "kernel_ms": kernel_ms, "all_render_kernels_ms": render_ms,
+            "clocks": m["clocks"],
+            "roofline": {"bound": "fp32", "achieved": ach_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": ach_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                         "kernel": m["dominant_kernel"], "kernel_ms": kernel_ms, "all_render_kernels_ms": m["render_ms"],
                          "peak_source": "measured in this run: rt_measure_fp32_peak (register FFMA microbenchmark); MEASURED_PEAKS.json has no FP32 figure",
                          "algorithmic": f"EXECUTED tests x canonical flop (SURVEY 8d): {F_BOX}/box, {F_TRI}/triangle, {F_SPH}/sphere, {F_BEAM_TRI}/beam-triangle test; "
                                         f"{int(counts['box_tests'])} box, {int(counts['triangle_tests'])} triangle, {int(counts['sphere_tests'])} sphere, "
                                         f"{int(counts['beam_triangle_tests'])} beam-triangle tests per frame, of which the primary pre-pass kernel's "
                                         f"{int(counts['prepass_box_tests'])} / {int(counts['prepass_triangle_tests'])} / {int(counts['prepass_sphere_tests'])} are left out",
                          "per_ray_traversal_equivalent": {
-                             "achieved": flops_ray / world / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                             "frac": flops_ray / world / (kernel_ms * 1e-3) / 1e12 / fp32_peak.value if fp32_peak.value else None,
+                             "achieved": m["flops_ray"] / world / (kernel_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                             "frac": m["flops_ray"] / world / (kernel_ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None,
                              "note": "the same frame's test counts when every shadow ray walks the BVH itself (RT_FLAG_PER_RAY_SHADOWS counter build: "
                                      f"{int(counts_ray['box_tests'])} box, {int(counts_ray['triangle_tests'])} triangle, {int(counts_ray['sphere_tests'])} sphere) "
                                      "over the measured kernel time: the work shadow beams avoid counts as done here, it does not in `achieved`"},
                          "traffic_source": traffic_src,
-                         "hbm": {"achieved": bytes_alg / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": bytes_alg / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                         "hbm": {"achieved": m["bytes_alg"] / world / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": m["bytes_alg"] / world / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                                  "note": ("algorithmic node/primitive bytes; the scene is L1/L2 resident, so this is cache not DRAM traffic"
                                           if flat.n_primitives * 64 < 64e6 else
                                           "algorithmic node/primitive bytes; the primitive array exceeds L2, part of this is DRAM traffic")}},
-            "wall_s_timed_region": wall,
+            "scenes": scenes,
+            "wall_s_timed_region": m["wall"],
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(flat, rc)
         emit(line)
-    dev.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -63,6 +63,11 @@ class Config(C.Structure):
     ]
 
 
+class SceneInfo(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint32), ("n_slots", C.c_uint32), ("bvh_depth", C.c_uint32), ("builder", C.c_uint32),
+                ("build_ms", C.c_double), ("upload_ms", C.c_double), ("device_bytes", C.c_uint64)]
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("total_ms", C.c_double), ("closest_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
@@ -97,6 +102,9 @@ def _declare(lib: C.CDLL) -> None:
         "rt_measure_fp32_peak": (i32, [i32, P(C.c_double)]),
         "rt_scene_create": (i32, [P(SceneDesc), i32, P(vp)]),
         "rt_scene_destroy": (None, [vp]),
+        "rt_scene_get_info": (i32, [vp, P(SceneInfo)]),
+        "rt_check_frame": (i32, [vp]),
+        "rt_last_kernel": (C.c_char_p, [vp]),
         "rt_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),
         "rt_render_progressive": (i32, [vp, P(Config), vp, vp, u32, vp, vp, P(Stats)]),
         "rt_render_device": (i32, [vp, P(Config), vp, vp, vp, P(Stats)]),

@@ -51,8 +51,14 @@ struct rt_scene {
     uint32_t h_params_next = 0;
     RenderParams d_params_host{};           // what d_params currently holds
     bool d_params_valid = false;
-    unsigned int *h_watchdog = nullptr;     // pinned: HeavyQueue::watchdog of the last frame
-    bool frame_has_watchdog = false;
+    unsigned int *d_watchdog = nullptr;     // sticky device word: != 0 when a bounded wait loop of direct_kernel gave up
+    unsigned int *h_watchdog = nullptr;     // pinned: its value after the last fetched frame
+    bool frame_has_watchdog = false;        // the frame being enqueued launches direct_kernel
+    bool watchdog_pending = false;          // a fetch has been enqueued and not been looked at yet
+    cudaEvent_t ev_watchdog = nullptr;      // recorded after that fetch
+    cudaStream_t last_stream = nullptr;     // stream of the previous call + event recorded at its end: a call on ANOTHER
+    cudaEvent_t ev_last = nullptr;          // stream first waits for it (the scratch buffers are shared)
+    bool has_last = false;
     float4 *heavy_scratch = nullptr;        // per deferred unit: M copies x 32 samples x 2 float4
     size_t heavy_scratch_cap = 0;
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
@@ -76,6 +82,8 @@ struct rt_scene {
     static constexpr uint32_t KERNEL_EVENT_RING = 64;
     cudaEvent_t kev[KERNEL_EVENT_RING][2] = {};
     uint64_t kev_count = 0;
+    char last_kernel[64] = "";
+    rt_scene_info info{};
 };
 
 static cudaEvent_t kernel_event(rt_scene *s, int which) {
@@ -113,6 +121,15 @@ static int validate_config(const rt_config *c) {
             return rt_fail(RT_ERR_INVALID_ARGUMENT, "anti-aliasing needs aa_table with 1..%d samples (got %u, table %u)", MAX_AA, S, c->aa_table_len);
         if ((c->flags & RT_FLAG_PACKET_SEMANTICS) && (S % 8))
             return rt_fail(RT_ERR_INVALID_ARGUMENT, "packet semantics need a multiple of 8 samples (got %u)", S);
+    }
+    {
+        // work items, sample indices and unit numbers are 32-bit on the device: reject frames that would wrap
+        const uint32_t S = (c->flags & RT_FLAG_ANTI_ALIASING) ? ((c->flags & RT_FLAG_PACKET_SEMANTICS) ? c->aa_table_len : c->aa_samples_per_pixel) : 1u;
+        const uint64_t tiles_x = (c->width + TILE_W - 1) / TILE_W, tiles_y = ((uint64_t)local_rows_of(c) + TILE_H - 1) / TILE_H;
+        const uint64_t items = tiles_x * tiles_y * (TILE_W * TILE_H) * std::max<uint64_t>(S, 1);
+        if (items >= (1ull << 31))
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu primary samples (limit 2^31); render it in row tiles",
+                           (unsigned long long)items);
     }
     if (c->light_multiplicator > 1 && (!c->light_clouds || c->n_light_clouds == 0))
         return rt_fail(RT_ERR_INVALID_ARGUMENT, "light_multiplicator %u needs light_clouds", c->light_multiplicator);
@@ -239,6 +256,9 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
                           uint64_t *launches) {
     fill_params(s, cfg, p);
     s->frame_has_watchdog = false;
+    // the scene's scratch buffers and cached tables are shared by all calls: a call on another stream than the
+    // previous one is ordered after it
+    if (s->has_last && s->last_stream != stream) CU_CHECK(cudaStreamWaitEvent(stream, s->ev_last, 0));
     size_t n_samples = (size_t)p.local_rows * p.width * p.S;
     int rc = grow(s->samples, s->samples_cap, std::max<size_t>(n_samples, 1) * sizeof(float4));
     if (rc) return rc;
@@ -323,6 +343,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         else
             render_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p, gp);
         CU_CHECK(cudaGetLastError());
+        snprintf(s->last_kernel, sizeof(s->last_kernel), "render_kernel<%s>", count ? "true" : "false");
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
         if (launches) *launches += 1;
@@ -331,6 +352,9 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         const uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);
         const uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
         if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
+        if ((uint64_t)warps_needed * passes >= (1ull << 32))
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu work units (limit 2^32); render it in row tiles",
+                           (unsigned long long)warps_needed * passes);
         {
             const size_t before = s->direct_cap;
             // one chained record per (light group, sample); the last group writes the sample itself
@@ -359,7 +383,8 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         uint32_t defer_below = 100;
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
-        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *);
+        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *,
+                                  unsigned int *);
         kernel_t kernel;
         if (count)
             kernel = beams ? (defer ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
@@ -379,17 +404,21 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
             pd.heavy_cap = HEAVY_CAP;
             if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
+            if (const char *e = getenv("RT_DEFER_ALL")) pd.defer_all = atoi(e) != 0;  // tests: every unit asks for deferral
             rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;
             CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter
             hq = s->heavy_queue;
-            s->frame_has_watchdog = true;
             if ((rc = upload_params(s, pd, stream))) return rc;
         }
         unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
         if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
         if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params);
+        snprintf(s->last_kernel, sizeof(s->last_kernel), "direct_kernel<%s,%s,%s>", count ? "true" : "false", beams ? "true" : "false",
+                 defer ? "true" : "false");
+        s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
+                                                  s->d_watchdog);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
         s->kev_count++;
@@ -402,18 +431,37 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
     return RT_OK;
 }
 
-// after the frame's kernels: fetch the device watchdog word (enqueue) / check it (after the stream is synchronised)
+// after the frame's kernels: fetch the sticky device watchdog word (enqueue) / look at it (after the fetch has completed)
 static int enqueue_watchdog_fetch(rt_scene *s, cudaStream_t stream) {
-    if (!s->frame_has_watchdog) return RT_OK;
-    if (!s->h_watchdog) CU_CHECK(cudaMallocHost((void **)&s->h_watchdog, sizeof(unsigned int)));
-    *s->h_watchdog = 0;
-    CU_CHECK(cudaMemcpyAsync(s->h_watchdog, &s->heavy_queue->watchdog, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+    if (s->frame_has_watchdog) {
+        CU_CHECK(cudaMemcpyAsync(s->h_watchdog, s->d_watchdog, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CU_CHECK(cudaEventRecord(s->ev_watchdog, stream));
+        s->watchdog_pending = true;
+        s->frame_has_watchdog = false;
+    }
+    // end of this call's work on `stream`: what a later call on another stream waits for
+    CU_CHECK(cudaEventRecord(s->ev_last, stream));
+    s->last_stream = stream;
+    s->has_last = true;
     return RT_OK;
 }
-static int check_watchdog(rt_scene *s) {
-    if (!s->frame_has_watchdog || !s->h_watchdog) return RT_OK;
-    s->frame_has_watchdog = false;
-    if (*s->h_watchdog) return rt_fail(RT_ERR_CUDA, "direct_kernel: a wait loop gave up (code %u); the frame is invalid", *s->h_watchdog);
+// block = false: only looks when the fetch has already completed (cheap poll at the start of the next call)
+static int check_watchdog(rt_scene *s, bool block) {
+    if (!s->watchdog_pending) return RT_OK;
+    if (block) {
+        CU_CHECK(cudaEventSynchronize(s->ev_watchdog));
+    } else {
+        cudaError_t q = cudaEventQuery(s->ev_watchdog);
+        if (q == cudaErrorNotReady) return RT_OK;
+        if (q != cudaSuccess) return rt_fail(RT_ERR_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(q));
+    }
+    s->watchdog_pending = false;
+    const unsigned int code = *s->h_watchdog;
+    if (code) {
+        *s->h_watchdog = 0;
+        cudaMemset(s->d_watchdog, 0, sizeof(unsigned int));  // reported: re-arm
+        return rt_fail(RT_ERR_CUDA, "direct_kernel: a wait loop gave up (code %u); a frame rendered since the last check is invalid", code);
+    }
     return RT_OK;
 }
 
@@ -446,6 +494,21 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float *out, int iters, f
     float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (r == 12345.678f) out[0] = r;  // keeps the chains alive
 }
+
+namespace {
+struct DevBufs {  // frees its device buffers on every exit path
+    std::vector<void *> ptrs;
+    ~DevBufs() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    template <typename T>
+    cudaError_t alloc(T **out, size_t bytes) {
+        cudaError_t e = cudaMalloc((void **)out, bytes);
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+}  // namespace
 
 extern "C" {
 
@@ -509,8 +572,10 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     if (!out_scene) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null out_scene");
     *out_scene = nullptr;
     rtb::FlatScene flat;
+    const auto t_build0 = std::chrono::steady_clock::now();
     int rc = rtb::build_flat_scene(desc, flat);
     if (rc) return rc;
+    const auto t_build1 = std::chrono::steady_clock::now();
     rc = select_device(device);
     if (rc) return rc;
     rt_scene *s = new (std::nothrow) rt_scene();
@@ -537,6 +602,13 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     s->d.box_pad = flat.box_pad;
     s->n_nodes = flat.n_nodes;
     s->n_prims = flat.n_prims;
+    s->info.n_nodes = flat.n_nodes;
+    s->info.n_slots = flat.n_prims;
+    s->info.bvh_depth = flat.max_depth;
+    s->info.builder = 0;
+    s->info.build_ms = std::chrono::duration<double, std::milli>(t_build1 - t_build0).count();
+    s->info.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build1).count();
+    s->info.device_bytes = (flat.nodes.size() + flat.prims.size() + flat.shade_n.size() + flat.mats.size() + flat.lights.size()) * sizeof(float);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(rt_fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"));
     s->sm_count = prop.multiProcessorCount;
@@ -550,7 +622,10 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
         s->ctas_per_sm_direct_count = 1;
     if (cudaMalloc((void **)&s->work_counter, sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->pass_counters, MAX_PASSES * sizeof(unsigned int)) != cudaSuccess || cudaMalloc((void **)&s->counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&s->ev0) != cudaSuccess ||
-        cudaEventCreate(&s->ev1) != cudaSuccess)
+        cudaEventCreate(&s->ev1) != cudaSuccess || cudaMalloc((void **)&s->d_watchdog, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(s->d_watchdog, 0, sizeof(unsigned int)) != cudaSuccess || cudaMallocHost((void **)&s->h_watchdog, sizeof(unsigned int)) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_watchdog, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming) != cudaSuccess)
         return fail(rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out_scene = s;
     return RT_OK;
@@ -559,7 +634,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->d_watchdog};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->h_params) cudaFreeHost(s->h_params);
@@ -568,6 +643,8 @@ void rt_scene_destroy(rt_scene *s) {
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_watchdog) cudaEventDestroy(s->ev_watchdog);
+    if (s->ev_last) cudaEventDestroy(s->ev_last);
     for (auto &pair : s->kev)
         for (cudaEvent_t e : pair)
             if (e) cudaEventDestroy(e);
@@ -582,6 +659,7 @@ int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *
     int rc = validate_config(cfg);
     if (rc) return rc;
     CU_CHECK(cudaSetDevice(s->device));
+    if ((rc = check_watchdog(s, false))) return rc;  // an earlier asynchronous frame that went wrong surfaces here at the latest
     cudaStream_t stream = (cudaStream_t)cuda_stream;  // NULL = the legacy default stream, as the caller asked
     auto t0 = std::chrono::steady_clock::now();
     RenderParams p;
@@ -589,12 +667,12 @@ int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *
     if (stats) CU_CHECK(cudaEventRecord(s->ev0, stream));
     rc = enqueue_render(s, cfg, p, (uint32_t *)d_out_argb, (uint8_t *)d_out_hit_mask, stream, &launches);
     if (rc) return rc;
+    if (stats) CU_CHECK(cudaEventRecord(s->ev1, stream));
+    if ((rc = enqueue_watchdog_fetch(s, stream))) return rc;
     if (stats) {
         memset(stats, 0, sizeof(*stats));
-        CU_CHECK(cudaEventRecord(s->ev1, stream));
-        if ((rc = enqueue_watchdog_fetch(s, stream))) return rc;
         CU_CHECK(cudaStreamSynchronize(stream));
-        if ((rc = check_watchdog(s))) return rc;
+        if ((rc = check_watchdog(s, true))) return rc;
         CU_CHECK(cudaEventSynchronize(s->ev1));
         float ms = 0;
         CU_CHECK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
@@ -609,11 +687,26 @@ int rt_render_device(rt_scene *s, const rt_config *cfg, void *d_out_argb, void *
     return RT_OK;
 }
 
+const char *rt_last_kernel(const rt_scene *s) { return s ? s->last_kernel : ""; }
+
+int rt_scene_get_info(const rt_scene *s, rt_scene_info *out) {
+    if (!s || !out) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_get_info: null argument");
+    *out = s->info;
+    return RT_OK;
+}
+
+int rt_check_frame(rt_scene *s) {
+    if (!s) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_check_frame: null scene");
+    CU_CHECK(cudaSetDevice(s->device));
+    return check_watchdog(s, true);
+}
+
 int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, rt_stats *stats) {
     if (!s || !out_argb) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null scene or output");
     int rc = validate_config(cfg);
     if (rc) return rc;
     CU_CHECK(cudaSetDevice(s->device));
+    if ((rc = check_watchdog(s, false))) return rc;
     auto t0 = std::chrono::steady_clock::now();
     const uint32_t rows = local_rows_of(cfg);
     const size_t n_pix = (size_t)rows * cfg->width;
@@ -634,7 +727,7 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
     if (n_pix) CU_CHECK(cudaMemcpyAsync(s->pinned_argb, s->slab_argb, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
     if ((rc = enqueue_watchdog_fetch(s, s->stream))) return rc;
     CU_CHECK(cudaStreamSynchronize(s->stream));
-    if ((rc = check_watchdog(s))) return rc;
+    if ((rc = check_watchdog(s, true))) return rc;
     // ImageBuffer semantics (reference src/renderer/mod.rs:116-125): only hit pixels are stored.  A slab pixel is
     // 0xFFrrggbb for a hit and 0 for a miss (resolve_kernel), so the hit mask is `pixel != 0`: no second copy.
     const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
@@ -745,20 +838,18 @@ int rt_trace_closest(rt_scene *s, uint32_t flags, const float *rays, uint32_t n,
     if (!s || (n && (!rays || !out_t || !out_prim))) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_trace_closest: null argument");
     if (!n) return RT_OK;
     CU_CHECK(cudaSetDevice(s->device));
+    DevBufs bufs;
     float *d_rays = nullptr, *d_t = nullptr;
     uint32_t *d_prim = nullptr;
-    CU_CHECK(cudaMalloc((void **)&d_rays, (size_t)n * 6 * sizeof(float)));
-    CU_CHECK(cudaMalloc((void **)&d_t, (size_t)n * sizeof(float)));
-    CU_CHECK(cudaMalloc((void **)&d_prim, (size_t)n * sizeof(uint32_t)));
+    CU_CHECK(bufs.alloc(&d_rays, (size_t)n * 6 * sizeof(float)));
+    CU_CHECK(bufs.alloc(&d_t, (size_t)n * sizeof(float)));
+    CU_CHECK(bufs.alloc(&d_prim, (size_t)n * sizeof(uint32_t)));
     CU_CHECK(cudaMemcpy(d_rays, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice));
     trace_closest_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d, flags, d_rays, n, d_t, d_prim);
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaStreamSynchronize(s->stream));
     CU_CHECK(cudaMemcpy(out_t, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     CU_CHECK(cudaMemcpy(out_prim, d_prim, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    cudaFree(d_rays);
-    cudaFree(d_t);
-    cudaFree(d_prim);
     return RT_OK;
 }
 
@@ -766,19 +857,17 @@ int rt_trace_shadow(rt_scene *s, uint32_t flags, const float *rays, const float 
     if (!s || (n && (!rays || !max_dist || !out))) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_trace_shadow: null argument");
     if (!n) return RT_OK;
     CU_CHECK(cudaSetDevice(s->device));
+    DevBufs bufs;
     float *d_rays = nullptr, *d_md = nullptr, *d_out = nullptr;
-    CU_CHECK(cudaMalloc((void **)&d_rays, (size_t)n * 6 * sizeof(float)));
-    CU_CHECK(cudaMalloc((void **)&d_md, (size_t)n * sizeof(float)));
-    CU_CHECK(cudaMalloc((void **)&d_out, (size_t)n * 5 * sizeof(float)));
+    CU_CHECK(bufs.alloc(&d_rays, (size_t)n * 6 * sizeof(float)));
+    CU_CHECK(bufs.alloc(&d_md, (size_t)n * sizeof(float)));
+    CU_CHECK(bufs.alloc(&d_out, (size_t)n * 5 * sizeof(float)));
     CU_CHECK(cudaMemcpy(d_rays, rays, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice));
     CU_CHECK(cudaMemcpy(d_md, max_dist, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
     trace_shadow_kernel<<<(n + 127) / 128, 128, 0, s->stream>>>(s->d, flags, d_rays, d_md, n, d_out);
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaStreamSynchronize(s->stream));
     CU_CHECK(cudaMemcpy(out, d_out, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost));
-    cudaFree(d_rays);
-    cudaFree(d_md);
-    cudaFree(d_out);
     return RT_OK;
 }
 

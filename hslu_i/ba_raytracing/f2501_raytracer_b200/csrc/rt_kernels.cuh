@@ -25,7 +25,7 @@ namespace rtd {
 // Occupancy sweep on B200 (profiles/README.md): the kernel is latency bound, 28 warps/SM at 72
 // registers (a few hundred bytes of spills) beats 16 warps/SM at 125 registers without spills by 13 %.
 #ifndef RT_EMPTY_LIST_SKIP
-#define RT_EMPTY_LIST_SKIP 0  // off until it has been through the GPU tests (see RT_SELF_CULL in rt_device.cuh)
+#define RT_EMPTY_LIST_SKIP 1  // a beam without candidates: no list walk (see RT_SELF_CULL in rt_device.cuh)
 #endif
 #ifndef RT_CTA_THREADS
 #define RT_CTA_THREADS 128
@@ -60,6 +60,7 @@ struct RenderParams {
     uint32_t tiles_x, n_items;
     uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
     uint32_t heavy_cap;    // direct_kernel: deferred units per launch (<= HEAVY_CAP; beyond: processed in place)
+    uint32_t defer_all;    // tests only (RT_DEFER_ALL): every unit asks for deferral
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
     uint4 *primary_hits;           // n_items: closest hit of every primary sample (primary_kernel): bits t, slot, prim, meta
     unsigned int *work_counter;
@@ -162,7 +163,7 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     }
     ShadowResult sh;
 #if RT_EMPTY_LIST_SKIP
-    // (next round) an empty candidate list: the query is "nothing on the segment" whatever the ray -- the whole
+    // an empty candidate list: the query is "nothing on the segment" whatever the ray -- the whole
     // warp skips the list walk when none of its lanes has a candidate
     if (MODE == 1 && n_cand == 0 && *last_occluder < 0) {
         if (COUNT) cn.shadow++;
@@ -635,19 +636,20 @@ struct HeavyQueue {
     unsigned int n_heavy;       // units on the list
     unsigned int next_task;     // next sub-task ticket: heavy index * M + copy
     unsigned int warps_done_a;  // warps that have left the unit loop (after that the list is final)
-    unsigned int watchdog;      // != 0: a wait loop gave up (code of the loop); the frame is invalid
     unsigned int unit_counter;  // direct_kernel's unit queue (here so that one memset resets everything)
-    unsigned int pad[3];
+    unsigned int pad[4];
     unsigned int done[HEAVY_CAP];  // finished sub-tasks
     unsigned int unit[HEAVY_CAP];  // unit + 1; 0 until written
 };
 RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
-// Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render
-// fails with RT_ERR_CUDA), never as a hung GPU.
+// Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render /
+// rt_check_frame fail with RT_ERR_CUDA), never as a hung GPU.  The watchdog word is STICKY: it is only reset by
+// the host after it has reported the error, so an asynchronous caller (rt_render_device without stats) that
+// checks late still sees a trip of any frame since its last check.
 constexpr uint32_t WAIT_SPINS = 1u << 23;   // plain polling loops (seconds)
 constexpr uint32_t WAIT_SLEEPS = 1u << 21;  // loops that sleep 1 us per poll (seconds)
-RT_DEV void watchdog_trip(HeavyQueue *hq, unsigned int code) {
-    if (hq) atomicMax(&hq->watchdog, code);
+RT_DEV void watchdog_trip(unsigned int *watchdog, unsigned int code) {
+    if (watchdog) atomicMax(watchdog, code);
 }
 
 // one sample of a batch, rebuilt from the primary pre-pass record (cheap next to its shadow rays)
@@ -708,7 +710,7 @@ RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float
 // that it does not weigh on the register allocation of the unit loop.
 template <bool COUNT>
 __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
-                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out) {
+                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog) {
     const RenderParams &p = *gp;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -727,17 +729,17 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
             const uint32_t want = t / p.M;
             for (uint32_t spins = 0;; spins++) {
                 if (spins > WAIT_SLEEPS) {
-                    watchdog_trip(hq, 1u);
+                    watchdog_trip(watchdog, 1u);
                     break;
                 }
                 const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
-                const unsigned int n = min(ld_volatile_u32(&hq->n_heavy), p.heavy_cap);
+                const unsigned int n = ld_volatile_u32(&hq->n_heavy);  // (never above heavy_cap: slots are reserved by CAS)
                 if (want < n) {
                     idx = want;
                     c = t - want * p.M;
                     for (uint32_t w = 0; (unit = ld_volatile_u32(&hq->unit[idx]) - 1u) == 0xFFFFFFFFu; w++)
                         if (w > WAIT_SPINS) {
-                            watchdog_trip(hq, 2u);
+                            watchdog_trip(watchdog, 2u);
                             idx = 0xFFFFFFFFu;
                             break;
                         }
@@ -781,7 +783,7 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                     sd = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].d);
                     ss = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].s);
                     if (++spins > WAIT_SPINS) {
-                        watchdog_trip(hq, 3u);
+                        watchdog_trip(watchdog, 3u);
                         break;
                     }
                 } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
@@ -811,13 +813,14 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
 #ifndef RT_DIRECT_MIN_CTAS
 #define RT_DIRECT_MIN_CTAS RT_MIN_CTAS_PER_SM
 #endif
-// puts `unit` on the heavy list (slot idx): marks its chain records so that the units that continue these
-// samples' sums defer themselves too, zeroes the samples of lanes that missed (last group), publishes
+// puts `unit` on the heavy list (slot idx): marks its chain records (the mark carries the slot: the unit that
+// continues these samples' sums defers itself too, into the slot after this one, which was reserved together with
+// it), zeroes the samples of lanes that missed (last group), publishes
 __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, float4 *sample, uint32_t unit, uint32_t idx, uint32_t deferred_tag,
                                         bool mark_chain, bool zero_sample) {
     if (mark_chain) {
         const float tag = __uint_as_float(deferred_tag);
-        st_relaxed_gpu(&own_rec->d, make_float4(0.0f, 0.0f, 0.0f, tag));
+        st_relaxed_gpu(&own_rec->d, make_float4(__uint_as_float(idx), 0.0f, 0.0f, tag));
         st_relaxed_gpu(&own_rec->s, make_float4(0.0f, 0.0f, 0.0f, tag));
     }
     if (zero_sample) *sample = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -835,7 +838,7 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
 template <bool COUNT, bool BEAM, bool DEFER>
 __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
                                                                                     unsigned int *counter, DirectState *state, HeavyQueue *hq,
-                                                                                    float4 *hscratch, const RenderParams *gp) {
+                                                                                    float4 *hscratch, const RenderParams *gp, unsigned int *watchdog) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const DScene &sc = p.sc;
@@ -878,6 +881,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         int n_cand = -1;
         int32_t last_occluder = -1;
         bool defer = false;  // this lane wants the unit deferred
+        uint32_t inherited_slot = 0xFFFFFFFFu;  // ... because its predecessor is on the heavy list: the slot reserved for this unit
         LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
         if (p.LM > 0) L = load_light(p, li0);
         if (r.hit) {
@@ -890,7 +894,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #endif
                 for (uint32_t spins = 0;; spins++) {
                     if (spins > WAIT_SPINS) {
-                        watchdog_trip(hq, 4u);
+                        watchdog_trip(watchdog, 4u);
                         break;
                     }
                     sd = ld_relaxed_gpu(&prev_rec->d);
@@ -899,6 +903,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     if (td == want && ts == want) break;
                     if (DEFER && td == (want | CHAIN_DEFERRED)) {  // the predecessor is on the heavy list: so is this unit
                         defer = true;
+                        inherited_slot = __float_as_uint(sd.x) + 1u;
                         break;
                     }
                 }
@@ -920,37 +925,43 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
                 if (DEFER) defer = n_cand == -1;  // overflow: M separate BVH walks, everybody else in the warp waiting
             }
+            if (DEFER && p.defer_all) defer = true;  // (tests)
         }
         if (DEFER && BEAM && deferring) {
             __syncwarp();
             const unsigned want_defer = __ballot_sync(FULL, defer);
             if (want_defer) {
-                unsigned int idx = 0;
-                if (lane == 0) idx = atomicAdd(&hq->n_heavy, 1u);
-                idx = __shfl_sync(FULL, idx, 0);
-                if (idx < p.heavy_cap) {
+                // A unit never waits for a deferred predecessor: either it inherits the slot that was reserved for it
+                // when the first unit of its chain was listed, or (fresh) it reserves slots for itself AND every later
+                // group of this batch at once -- all or nothing, so the list never holds a unit whose successors cannot
+                // follow it.  No room: processed in place (its predecessor is not on the list: nothing to wait for).
+                const unsigned inherit = __ballot_sync(FULL, inherited_slot != 0xFFFFFFFFu);
+                unsigned int idx = 0xFFFFFFFFu;
+                if (inherit) {
+                    idx = __shfl_sync(FULL, inherited_slot, __ffs(inherit) - 1);
+                } else {
+                    if (lane == 0) {
+                        const unsigned int k = n_groups - group_index;
+                        unsigned int old = ld_volatile_u32(&hq->n_heavy);
+                        for (;;) {
+                            if (old + k > p.heavy_cap) break;
+                            const unsigned int seen = atomicCAS(&hq->n_heavy, old, old + k);
+                            if (seen == old) {
+                                idx = old;
+                                break;
+                            }
+                            old = seen;
+                        }
+                    }
+                    idx = __shfl_sync(FULL, idx, 0);
+                }
+                if (idx != 0xFFFFFFFFu) {
                     defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (frame_tag + group_index) | CHAIN_DEFERRED, !last && r.hit,
                                last && r.valid && !r.hit);
 #ifdef RT_DBG_TAIL
                     dbg_helped++;
 #endif
                     continue;
-                }
-                // the list is full: process in place (a deferred predecessor is finished by phase B: wait for it)
-                if (r.hit && group_index > 0) {
-                    const uint32_t want = frame_tag + group_index - 1u;
-                    float4 sd, ss;
-                    uint32_t spins = 0;
-                    do {
-                        sd = ld_relaxed_gpu(&prev_rec->d);
-                        ss = ld_relaxed_gpu(&prev_rec->s);
-                        if (++spins > WAIT_SPINS) {
-                            watchdog_trip(hq, 5u);
-                            break;
-                        }
-                    } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
-                    sum_d = f3(sd.x, sd.y, sd.z);
-                    sum_s = f3(ss.x, ss.y, ss.z);
                 }
             }
         }
@@ -1005,7 +1016,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        finish_heavy_units<COUNT>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr);
+        finish_heavy_units<COUNT>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif

@@ -72,6 +72,10 @@ class TiledRenderer:
             L.check(lib.rt_place_tiles(C.byref(cfg), self.gathered.data_ptr(), self.pad_rows * self.width, self.frame.data_ptr(),
                                        self.frame_mask.data_ptr() if with_mask else None, stream))
 
+    def check(self) -> None:
+        """rt_check_frame: the frames enqueued by render_local() since the last check are valid (raises otherwise)."""
+        self.scene.check()
+
     def step(self) -> None:
         self.render_local()
         self.gather()

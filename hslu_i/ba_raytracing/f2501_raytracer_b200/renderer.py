@@ -140,6 +140,20 @@ class DeviceScene:
         L.check(self._lib.rt_render_device(self._h, C.byref(rc.cfg), d_argb, d_mask, stream, C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
 
+    def check(self) -> None:
+        """rt_check_frame: waits for the frames enqueued with render_device() and raises if one of them is invalid."""
+        L.check(self._lib.rt_check_frame(self._h))
+
+    def dominant_kernel_name(self) -> str:
+        """rt_last_kernel: the dominant kernel the last render call launched."""
+        return (self._lib.rt_last_kernel(self._h) or b"").decode()
+
+    def bvh_info(self) -> dict:
+        """rt_scene_get_info: what rt_scene_create built and where its time went."""
+        info = L.SceneInfo()
+        L.check(self._lib.rt_scene_get_info(self._h, C.byref(info)))
+        return {k: getattr(info, k) for k, _ in info._fields_}
+
     def kernel_times(self, n: int = 64) -> np.ndarray:
         """rt_kernel_times: device ms of the dominant kernel of the last (up to 64) render calls."""
         out = np.zeros(max(n, 1), np.float32)

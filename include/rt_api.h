@@ -170,6 +170,24 @@ int rt_measure_fp32_peak(int device, double *out_tflops);
 int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene);
 void rt_scene_destroy(rt_scene *scene);
 
+/* What rt_scene_create built: sizes of the flattened arrays and where its time went (measurement only). */
+typedef struct rt_scene_info {
+    uint32_t n_nodes;        /* BVH4 nodes (128 B each) */
+    uint32_t n_slots;        /* primitive slots = references (64 B each; >= primitives: large triangles are split) */
+    uint32_t bvh_depth;      /* deepest BVH4 level */
+    uint32_t builder;        /* 0 = host (binned SAH, multi-threaded), 1 = device (LBVH) */
+    double build_ms;         /* BVH build + flattening */
+    double upload_ms;        /* host-to-device copies (0 for the device builder: built in place) */
+    uint64_t device_bytes;   /* nodes + slots + normals + materials + lights */
+} rt_scene_info;
+int rt_scene_get_info(const rt_scene *scene, rt_scene_info *out);
+
+/* Threading / streams: an rt_scene owns scratch buffers and cached sampler tables that every render call on it
+ * uses, so it is NOT re-entrant: call into one rt_scene from one host thread at a time (the reference renders from
+ * a single render thread, src/main.rs:330-340).  Calls may use different CUDA streams (rt_render uses the scene's
+ * own stream, rt_render_device the caller's): the library orders a call after the previous call on the same scene
+ * with an event, so mixing them needs no device synchronisation by the caller. */
+
 /* Replaces RaytracerRenderer::render (raytracer_renderer.rs:1369-1378).  `out_argb` is the
  * ImageBuffer storage: width*height u32, row-major, 0xFFRRGGBB for hit pixels, miss pixels
  * untouched (renderer/mod.rs:116-125) unless RT_FLAG_ZERO_MISSES.  `out_hit_mask` (optional,
@@ -194,6 +212,16 @@ int rt_render_progressive(rt_scene *scene, const rt_config *cfg, uint32_t *out_a
  * `stats` is non-NULL (then it synchronises to fill it). */
 int rt_render_device(rt_scene *scene, const rt_config *cfg, void *d_out_argb, void *d_out_hit_mask,
                      void *cuda_stream, rt_stats *stats);
+
+/* Validity of the frames enqueued with rt_render_device(stats == NULL): waits for the last one and returns
+ * RT_ERR_CUDA if a bounded wait loop of the direct-lighting kernel gave up in ANY frame since the last check
+ * (the device-side flag is sticky).  rt_render and rt_render_device(stats != NULL) check before they return; the
+ * next render call on the scene also reports a failed earlier frame.  Call it before consuming asynchronous
+ * output (e.g. before a gather). */
+int rt_check_frame(rt_scene *scene);
+
+/* Name of the dominant kernel (direct_kernel<...> / render_kernel<...>) the last render call launched. */
+const char *rt_last_kernel(const rt_scene *scene);
 
 /* Device durations (ms, CUDA events on the launching stream) of the DOMINANT kernel -- direct_kernel
  * (no bounces) or render_kernel -- of the last min(n, 64) render calls on this scene, oldest first;

@@ -1109,7 +1109,9 @@ int oracle_render(const OSceneDesc *desc, const OConfig *cfg, int mode, int thre
         Renderer r(sc, *cfg, mode);
         std::vector<float> off;
         if (cfg->flags & F_AA) r.aa_offsets(off);
-        const uint32_t CH = 64;
+        // chunk of the shared pixel queue: small enough that a short pixel list still keeps every thread busy
+        // (>= 8 chunks per thread), at most 64 pixels
+        const uint32_t CH = std::max<uint32_t>(1u, std::min<uint32_t>(64u, n_pixels / (8u * (uint32_t)threads)));
         for (;;) {
             uint32_t b = next.fetch_add(CH);
             if (b >= n_pixels) break;

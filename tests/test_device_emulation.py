@@ -41,13 +41,13 @@ def _build_emu(lib_name, defines=()):
     return lib
 
 
-@pytest.fixture(scope="module", params=["product", "next"])
+@pytest.fixture(scope="module", params=["product", "round1_filter"])
 def emu(request):
-    """"product": the device code as the product builds it.  "next": with the compile-time switches that are off in
-    the product until they have been through the GPU tests (RT_SPHERE_MISS_CULL, RT_SELF_CULL), so that they are ready to flip."""
+    """"product": the device code as the product builds it (beam-filter switches RT_SPHERE_MISS_CULL / RT_SELF_CULL on).
+    "round1_filter": the same code with both switches off (the round-1 filter), which stays buildable for A/B runs."""
     if request.param == "product":
         return _build_emu("libdevice_emu.so")
-    return _build_emu("libdevice_emu_next.so", ("-DRT_SPHERE_MISS_CULL=1", "-DRT_SELF_CULL=1"))
+    return _build_emu("libdevice_emu_r1.so", ("-DRT_SPHERE_MISS_CULL=0", "-DRT_SELF_CULL=0"))
 
 
 def ptr(a):

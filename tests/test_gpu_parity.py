@@ -343,6 +343,46 @@ def test_deferred_units_are_bit_identical(pkg, scenes, monkeypatch):
         assert np.array_equal(a.buffer, c.buffer) and np.array_equal(a.hit_mask, c.hit_mask)
 
 
+@pytest.mark.parametrize("cap", ["16384", "3000", "37", "0"])
+def test_deferral_never_blocks_when_the_list_fills_up(pkg, scenes, monkeypatch, cap):
+    """Every unit of the launch asks for deferral (RT_DEFER_ALL, a test hook) -- tens of thousands of units against a
+    heavy list of `cap` slots, i.e. far more than one per resident warp take the list-full path.  A unit reserves
+    slots for itself and all later groups of its batch at once or is processed in place, so no unit ever waits for a
+    listed predecessor it cannot follow: the frame completes (no watchdog error) and is the in-place image bit for bit."""
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 2, width=384, height=320, n_light_clouds=512)
+    monkeypatch.setenv("RT_DEFER_BELOW", "0")
+    ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    monkeypatch.setenv("RT_DEFER_BELOW", "1000000")
+    monkeypatch.setenv("RT_DEFER_ALL", "1")
+    monkeypatch.setenv("RT_HEAVY_CAP", cap)
+    got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))   # raises RtError if a wait loop gave up
+    assert ref.hit_mask.any() and np.array_equal(ref.buffer, got.buffer) and np.array_equal(ref.hit_mask, got.hit_mask)
+
+
+def test_asynchronous_frames_are_checked(pkg, scenes):
+    """rt_render_device(stats = NULL) returns after enqueueing; rt_check_frame waits for the frame and reports the
+    device watchdog (here: a valid frame, on a caller stream and then on the scene's own stream without a device
+    synchronisation in between -- the library orders the two)."""
+    torch = pytest.importorskip("torch")
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 4, width=384, height=320, n_light_clouds=512)
+    host, _ = dev.render(pkg.RenderConfig.from_features(feat, 4, width=384, height=320, n_light_clouds=512, extra_flags=pkg._lib.FLAG_ZERO_MISSES))
+    slab = torch.zeros(384 * 320, dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        dev.render_device(rc, slab.data_ptr(), None, side.cuda_stream)   # async, caller's stream
+    again, _ = dev.render(pkg.RenderConfig.from_features(feat, 4, width=384, height=320, n_light_clouds=512, extra_flags=pkg._lib.FLAG_ZERO_MISSES))
+    dev.check()
+    side.synchronize()
+    assert np.array_equal(slab.cpu().numpy().view(np.uint32), host.buffer) and np.array_equal(again.buffer, host.buffer)
+    assert dev.dominant_kernel_name().startswith("direct_kernel<false,true,")
+    info = dev.bvh_info()
+    assert info["n_nodes"] > 1000 and info["n_slots"] >= flat.n_primitives and info["build_ms"] > 0
+
+
 def test_place_tiles_and_kernel_times(pkg, scenes):
     """rt_place_tiles: all ranks' gathered slabs -> frame + hit mask in one launch (mask = pixel != 0);
     rt_kernel_times: one duration per render call."""
