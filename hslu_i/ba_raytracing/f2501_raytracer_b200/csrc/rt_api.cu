@@ -795,6 +795,21 @@ int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb,
     return RT_OK;
 }
 
+int rt_frame_constants(const rt_config *cfg, float *out_constants, float *out_offsets, uint32_t *out_samples) {
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    rt_scene none;  // fill_params only copies the (empty) device scene description
+    RenderParams p;
+    fill_params(&none, cfg, p);
+    if (out_constants) {
+        const float k[8] = {p.w2s_w, p.w2s_h, p.w2s_d, p.focus_x, p.focus_y, p.focus_z, p.eps_d, p.sample_scale};
+        memcpy(out_constants, k, sizeof(k));
+    }
+    if (out_offsets) memcpy(out_offsets, p.aa_off, sizeof(float) * 2 * p.S);
+    if (out_samples) *out_samples = p.S;
+    return RT_OK;
+}
+
 int rt_kernel_times(rt_scene *s, uint32_t n, float *out_ms, uint32_t *out_n) {
     if (!s || !out_ms || !out_n) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_kernel_times: null argument");
     CU_CHECK(cudaSetDevice(s->device));

@@ -252,6 +252,15 @@ int rt_trace_closest(rt_scene *scene, uint32_t flags, const float *rays, uint32_
 int rt_trace_shadow(rt_scene *scene, uint32_t flags, const float *rays, const float *max_dist,
                     uint32_t n, float *out);
 
+/* Debug/parity (host only, no device needed): the per-frame constants and anti-aliasing sample offsets the kernels
+ * receive for `cfg`, evaluated in f32 exactly as for a render call.
+ * out_constants[8] = WINDOW_TO_SCENE_{WIDTH,HEIGHT,DEPTH}_FACTOR, RENDER_RAY_FOCUS.xyz, default_epsilon_distance
+ * component, 1/samples (src/lib.rs:73-92, src/vector.rs:697-700, raytracer_renderer.rs:936-937).
+ * out_offsets: *out_samples x [dx, dy] added to the pixel's scene coordinate for sample i
+ * (raytracer_renderer.rs:876-916,1021-1138: bias direction i % 8 in packet mode, always the first one otherwise);
+ * room for 24 pairs.  Either output may be NULL. */
+int rt_frame_constants(const rt_config *cfg, float *out_constants, float *out_offsets, uint32_t *out_samples);
+
 /* Debug/parity: builds the BVH of `desc` on the host only (no device needed) and returns an FNV-1a digest
  * of the flattened node / primitive / normal arrays, the BVH4 node count and depth.  The build is
  * multi-threaded (all host threads; RT_BVH_THREADS overrides) and the result must not depend on the

@@ -191,6 +191,26 @@ def test_test_scene_with_everything_on(pkg, oracle_mod, scenes):
                seed=9, width=380, height=316, n_light_clouds=256)
 
 
+@pytest.mark.parametrize("scene_name,features,kw", [
+    ("semesterbild", "simd_render,soft_shadows", {}),                                                   # direct_kernel, M = 10, full 768x640 frame
+    ("semesterbild", "simd_render,soft_shadows,realistic", dict(width=384, height=320, n_light_clouds=512)),  # render_kernel
+    ("test_scene", "simd_render,backface_culling,soft_shadows,medium_resolution", dict(n_light_clouds=256, stride=2)),  # 36-px edge chunk: 4-px tail packet
+])
+def test_packet_path_without_aa_shares_one_cloud_per_packet(pkg, oracle_mod, scenes, scene_name, features, kw):
+    """simd_render + soft_shadows WITHOUT anti-aliasing: the reference builds ONE light cloud per 8-pixel packet
+    (raytracer_renderer.rs:1274-1280, the `preprocess` call sits outside the lanes) instead of one per pixel.
+    GPU vs oracle, which keys the cloud by (x / 8, y)."""
+    kw = dict(kw)
+    stride = kw.pop("stride", 1)
+    flat, dev, rc, buf, cnt, d = full_frame(pkg, oracle_mod, scenes, scene_name, features, seed=6, stride=stride, **kw)
+    assert rc.samples_per_pixel == 1 and rc.cfg.light_multiplicator == 10
+    # and it matters: keyed per pixel (the scalar path's rule) the penumbrae come out differently
+    scalar_feat = features.replace("simd_render,", "")
+    flat2, dev2 = scenes(scene_name, scalar_feat)
+    other, _ = dev2.render(pkg.RenderConfig.from_features(scalar_feat, 6, **kw))
+    assert np.array_equal(other.hit_mask, buf.hit_mask) and not np.array_equal(other.buffer, buf.buffer)
+
+
 def test_large_synthetic_mesh(pkg, oracle_mod):
     """BASELINE configs[4] at reduced size: semesterbild objects + a 524 288-triangle relief, bounces,
     AA and soft shadows; every 7th pixel of a 405x337 frame, plus raw queries against the big BVH."""
@@ -215,6 +235,59 @@ def test_large_synthetic_mesh(pkg, oracle_mod):
         assert_image_parity(buf, o_argb, o_mask, pix)
     finally:
         dev.close()
+
+
+def test_c5_at_the_benchmarked_size(pkg, oracle_mod):
+    """BASELINE configs[4] at the size bench.py measures: 4 194 304-triangle relief + semesterbild objects,
+    `extreme_quality,realistic,high_resolution,simd_render` = 1620x1350, 24 samples, 140 shadow rays, depth 21/21.
+    The BVH of this scene is deeper than anything the reduced test builds (depth-bounded median fallback, large-triangle
+    cells next to 4 M tiny triangles).  Compared with the oracle's BVH mode: 10^5 raw closest-hit and shadow queries
+    (primitive, distance and occlusion exact) and a 2 400-pixel subsample of the rendered frame (hit mask exact,
+    +-1 LSB on >= 99.9 %)."""
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+    feat = "extreme_quality,realistic,high_resolution,simd_render"
+    flat = large_mesh_scene(feat).flatten()
+    assert len(flat.triangles) == 2 * 2048 * 1024 + 48
+    dev = pkg.DeviceScene(flat)
+    try:
+        assert dev.bvh_info()["n_slots"] >= flat.n_primitives
+        rng = np.random.default_rng(40)
+        rays = random_rays(rng, 100000)
+        # half of the rays aimed at the relief from the camera side, so that most of them end in the fine mesh
+        rays[::2, :3] = rng.uniform([0.1, 0.1, -0.5], [0.9, 0.7, 0.2], (50000, 3)).astype(np.float32)
+        rays[::2, 3:] = rng.uniform([0.1, 0.05, 0.7], [0.9, 0.8, 0.95], (50000, 3)).astype(np.float32) - rays[::2, :3]
+        t_g, p_g = dev.trace_closest(rays)
+        t_o, p_o = oracle_mod.trace_closest(flat.desc(), rays, 0, oracle_mod.BVH)
+        assert np.array_equal(p_g, p_o) and np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))
+        assert (p_o >= 9 + 48).mean() > 0.3  # the relief itself is hit
+        md = rng.uniform(0.05, 2.5, len(rays)).astype(np.float32)
+        s_g = dev.trace_shadow(rays, md)
+        s_o = oracle_mod.trace_shadow(flat.desc(), rays, md, 0, oracle_mod.BVH)
+        assert np.array_equal(s_g[:, 0], s_o[:, 0])
+        free = s_o[:, 0] == 0
+        assert np.allclose(s_g[free, 1:], s_o[free, 1:], rtol=0, atol=2e-6) and 0.05 < (~free).mean() < 0.95
+        rc = pkg.RenderConfig.from_features(feat, 6)
+        W, H = rc.cfg.width, rc.cfg.height
+        assert (W, H, rc.samples_per_pixel, rc.cfg.light_multiplicator) == (1620, 1350, 24, 28)
+        buf, _ = dev.render(rc)
+        ys, xs = np.mgrid[13:H:27, 11:W:34]   # 50 x 48 pixels
+        pix = (ys * W + xs).astype(np.uint32).ravel()
+        assert len(pix) >= 2400
+        o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+        assert_image_parity(buf, o_argb, o_mask, pix)
+        assert 0.5 < o_mask[pix].mean() < 1.0
+    finally:
+        dev.close()
+
+
+def test_c3_headline_full_frame(pkg, oracle_mod, scenes):
+    """The headline frame, EVERY pixel (491 520 pixels x 16 samples x 96 rays against the oracle's BVH mode)."""
+    flat, dev, rc, buf, cnt, d = full_frame(pkg, oracle_mod, scenes, "semesterbild", "high_quality,simd_render", seed=0, stride=1)
+    assert (d == 0).mean() > 0.999
+    rcc = pkg.RenderConfig.from_features("high_quality,simd_render", 0, extra_flags=pkg._lib.FLAG_COUNT_WORK)
+    _, st = dev.render(rcc)
+    assert (st["closest_rays"], st["shadow_rays"]) == (cnt["closest_rays"], cnt["shadow_rays"])
 
 
 # ---------------------------------------------------------------- properties at full size
