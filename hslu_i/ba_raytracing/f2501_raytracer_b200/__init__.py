@@ -8,10 +8,10 @@ there is no CPU, PyTorch or oracle fallback on the product path.
 from . import _lib
 from ._lib import RtError, load
 from .output import FileOutput
-from .renderer import DeviceScene, ImageBuffer, RaytracerRenderer, RenderConfig
+from .renderer import DeviceScene, ImageBuffer, MultiDeviceScene, RaytracerRenderer, RenderConfig
 from .scene import FlatScene, Mesh, Scene, example_scene, material
 
 __all__ = [
-    "DeviceScene", "FileOutput", "FlatScene", "ImageBuffer", "Mesh", "RaytracerRenderer", "RenderConfig", "RtError", "Scene",
+    "DeviceScene", "FileOutput", "FlatScene", "ImageBuffer", "Mesh", "MultiDeviceScene", "RaytracerRenderer", "RenderConfig", "RtError", "Scene",
     "example_scene", "load", "material",
 ]

@@ -109,6 +109,11 @@ def _declare(lib: C.CDLL) -> None:
         "rt_render_progressive": (i32, [vp, P(Config), vp, vp, u32, vp, vp, P(Stats)]),
         "rt_render_device": (i32, [vp, P(Config), vp, vp, vp, P(Stats)]),
         "rt_frame_constants": (i32, [P(Config), vp, vp, P(u32)]),
+        "rt_multi_create": (i32, [P(SceneDesc), vp, u32, P(vp)]),
+        "rt_multi_destroy": (None, [vp]),
+        "rt_multi_device_count": (u32, [vp]),
+        "rt_multi_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),
+        "rt_multi_get_info": (i32, [vp, P(SceneInfo), P(u32)]),
         "rt_kernel_times": (i32, [vp, u32, vp, P(u32)]),
         "rt_tile_local_rows": (u32, [P(Config)]),
         "rt_tile_row": (u32, [P(Config), u32]),

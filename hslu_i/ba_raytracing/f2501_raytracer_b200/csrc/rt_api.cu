@@ -253,7 +253,7 @@ static int upload_params(rt_scene *s, const RenderParams &p, cudaStream_t stream
 
 // enqueue render + resolve on `stream`; slab outputs are device pointers
 static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, uint32_t *d_argb, uint8_t *d_mask, cudaStream_t stream,
-                          uint64_t *launches) {
+                          uint64_t *launches, bool to_frame = false) {
     fill_params(s, cfg, p);
     s->frame_has_watchdog = false;
     // the scene's scratch buffers and cached tables are shared by all calls: a call on another stream than the
@@ -425,7 +425,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         if (launches) *launches += 1;
     }
     uint32_t n_pix = p.local_rows * p.width;
-    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask);
+    resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask, to_frame ? 1 : 0);
     CU_CHECK(cudaGetLastError());
     if (launches) *launches += 1;
     return RT_OK;
@@ -510,6 +510,8 @@ struct DevBufs {  // frees its device buffers on every exit path
 };
 }  // namespace
 
+static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_ms, rt_scene **out_scene);
+
 extern "C" {
 
 int rt_measure_fp32_peak(int device, double *out_tflops) {
@@ -575,8 +577,18 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     const auto t_build0 = std::chrono::steady_clock::now();
     int rc = rtb::build_flat_scene(desc, flat);
     if (rc) return rc;
+    const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+    return scene_from_flat(flat, device, build_ms, out_scene);
+}
+
+}  // extern "C"
+
+// uploads a flattened scene to `device` and allocates the per-scene scratch (the second half of rt_scene_create;
+// rt_multi_create builds the BVH once and runs this once per device)
+static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_ms, rt_scene **out_scene) {
+    *out_scene = nullptr;
     const auto t_build1 = std::chrono::steady_clock::now();
-    rc = select_device(device);
+    int rc = select_device(device);
     if (rc) return rc;
     rt_scene *s = new (std::nothrow) rt_scene();
     if (!s) return rt_fail(RT_ERR_OUT_OF_MEMORY, "out of host memory");
@@ -606,7 +618,7 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     s->info.n_slots = flat.n_prims;
     s->info.bvh_depth = flat.max_depth;
     s->info.builder = 0;
-    s->info.build_ms = std::chrono::duration<double, std::milli>(t_build1 - t_build0).count();
+    s->info.build_ms = build_ms;
     s->info.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build1).count();
     s->info.device_bytes = (flat.nodes.size() + flat.prims.size() + flat.shade_n.size() + flat.mats.size() + flat.lights.size()) * sizeof(float);
     cudaDeviceProp prop;
@@ -630,6 +642,8 @@ int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene)
     *out_scene = s;
     return RT_OK;
 }
+
+extern "C" {
 
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
@@ -883,6 +897,336 @@ int rt_trace_shadow(rt_scene *s, uint32_t flags, const float *rays, const float 
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaStreamSynchronize(s->stream));
     CU_CHECK(cudaMemcpy(out, d_out, (size_t)n * 5 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RT_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================================
+// Multi-GPU inside ONE process (rt_multi_*): what a Rust host that binds this library gets when the
+// box has several B200s.  The reference partitions the frame inside render() over a rayon pool
+// (src/image_buffer.rs:48-97); here the partition is interleaved row tiles over the devices (tile t ->
+// device t % N, scene + BVH replicated, BVH built once), one host worker thread per device so that
+// all devices are launched concurrently, and the "gather" is fused into the last kernel of the
+// frame: every device's resolve_kernel stores its pixels straight into the full frame on device 0
+// through NVLink peer memory (P2P stores) -- no slab, no collective call, no placement pass.  Device
+// 0's stream waits for the other devices' events and copies the frame to the host.  A device without
+// peer access to device 0 falls back to its own slab + device-to-host copy.
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+
+namespace {
+class WorkerPool {  // n persistent threads; run(job) executes job(r) on thread r for every r and waits
+   public:
+    explicit WorkerPool(int n) : n_(n) {
+        for (int r = 0; r < n; r++) threads_.emplace_back([this, r] { loop(r); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void run(const std::function<void(int)> &job) {
+        std::unique_lock<std::mutex> lk(m_);
+        job_ = &job;
+        pending_ = n_;
+        gen_++;
+        cv_work_.notify_all();
+        cv_done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+   private:
+    void loop(int r) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                job = job_;
+            }
+            (*job)(r);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)> *job_ = nullptr;
+    uint64_t gen_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+}  // namespace
+
+struct rt_multi {
+    std::vector<int> devices;
+    std::vector<rt_scene *> scenes;     // one replica per device
+    std::vector<char> peer;             // device r can store into device 0's memory (r = 0: trivially)
+    std::vector<cudaEvent_t> done;      // device r's share of the frame has been written
+    std::vector<uint32_t *> slab;       // fallback without peer access: compact slab on device r ...
+    std::vector<size_t> slab_cap;
+    std::vector<uint32_t *> slab_host;  // ... and its pinned host copy
+    std::vector<size_t> slab_host_cap;
+    uint32_t *frame = nullptr;          // device 0: the full frame
+    size_t frame_cap = 0;
+    uint32_t *frame_host = nullptr;     // pinned
+    size_t frame_host_cap = 0;
+    cudaStream_t stream0 = nullptr;
+    std::unique_ptr<WorkerPool> pool;
+    double build_ms = 0, upload_ms = 0;
+};
+
+static void multi_free(rt_multi *m) {
+    if (!m) return;
+    m->pool.reset();
+    for (size_t r = 0; r < m->devices.size(); r++) {
+        cudaSetDevice(m->devices[r]);
+        if (r < m->done.size() && m->done[r]) cudaEventDestroy(m->done[r]);
+        if (r < m->slab.size() && m->slab[r]) cudaFree(m->slab[r]);
+        if (r < m->slab_host.size() && m->slab_host[r]) cudaFreeHost(m->slab_host[r]);
+        if (r < m->scenes.size() && m->scenes[r]) rt_scene_destroy(m->scenes[r]);
+    }
+    if (!m->devices.empty()) cudaSetDevice(m->devices[0]);
+    if (m->frame) cudaFree(m->frame);
+    if (m->frame_host) cudaFreeHost(m->frame_host);
+    if (m->stream0) cudaStreamDestroy(m->stream0);
+    delete m;
+}
+
+extern "C" {
+
+int rt_multi_create(const rt_scene_desc *desc, const int *devices, uint32_t n_devices, rt_multi **out) {
+    if (!out) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_create: null out");
+    *out = nullptr;
+    const int visible = rt_device_count();
+    if (visible == 0) return rt_fail(RT_ERR_NO_DEVICE, "no CUDA device available; librt_b200 has no CPU fallback");
+    if (n_devices == 0) n_devices = (uint32_t)visible;  // 0 = every visible device
+    if (n_devices > 64) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_create: %u devices", n_devices);
+    rt_multi *m = new (std::nothrow) rt_multi();
+    if (!m) return rt_fail(RT_ERR_OUT_OF_MEMORY, "out of host memory");
+    for (uint32_t r = 0; r < n_devices; r++) {
+        const int d = devices ? devices[r] : (int)r;
+        if (d < 0 || d >= visible) {
+            multi_free(m);
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_create: device %d out of range (0..%d)", d, visible - 1);
+        }
+        for (int seen : m->devices)
+            if (seen == d) {
+                multi_free(m);
+                return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_create: device %d listed twice", d);
+            }
+        m->devices.push_back(d);
+    }
+    // the BVH is built once, on the host, and uploaded to every device by its own worker thread
+    rtb::FlatScene flat;
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = rtb::build_flat_scene(desc, flat);
+    if (rc) {
+        multi_free(m);
+        return rc;
+    }
+    m->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const uint32_t n = n_devices;
+    m->scenes.assign(n, nullptr);
+    m->peer.assign(n, 0);
+    m->done.assign(n, nullptr);
+    m->slab.assign(n, nullptr);
+    m->slab_cap.assign(n, 0);
+    m->slab_host.assign(n, nullptr);
+    m->slab_host_cap.assign(n, 0);
+    m->pool.reset(new WorkerPool((int)n));
+    std::vector<int> rcs(n, RT_OK);
+    std::vector<std::string> errs(n);
+    const auto t1 = std::chrono::steady_clock::now();
+    m->pool->run([&](int r) {
+        int rc2 = scene_from_flat(flat, m->devices[r], m->build_ms, &m->scenes[r]);
+        if (!rc2 && cudaEventCreateWithFlags(&m->done[r], cudaEventDisableTiming) != cudaSuccess) rc2 = rt_fail(RT_ERR_CUDA, "cudaEventCreate failed");
+        if (!rc2) {
+            if (r == 0) {
+                m->peer[r] = 1;
+            } else {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, m->devices[r], m->devices[0]) == cudaSuccess && can) {
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(m->devices[0], 0);
+                    if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) m->peer[r] = 1;
+                }
+                cudaGetLastError();  // (an "already enabled" answer must not linger as the thread's last error)
+                if (getenv("RT_MULTI_NO_PEER")) m->peer[r] = 0;  // tests: the fallback path
+            }
+        }
+        rcs[r] = rc2;
+        if (rc2) errs[r] = rt_last_error();
+    });
+    m->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    for (uint32_t r = 0; r < n; r++)
+        if (rcs[r]) {
+            const int code = rcs[r];
+            const std::string msg = errs[r];
+            multi_free(m);
+            return rt_fail(code, "rt_multi_create: device %u: %s", r, msg.c_str());
+        }
+    cudaSetDevice(m->devices[0]);
+    if (cudaStreamCreateWithFlags(&m->stream0, cudaStreamNonBlocking) != cudaSuccess) {
+        multi_free(m);
+        return rt_fail(RT_ERR_CUDA, "rt_multi_create: stream creation failed");
+    }
+    *out = m;
+    return RT_OK;
+}
+
+void rt_multi_destroy(rt_multi *m) { multi_free(m); }
+
+uint32_t rt_multi_device_count(const rt_multi *m) { return m ? (uint32_t)m->devices.size() : 0; }
+
+int rt_multi_get_info(const rt_multi *m, rt_scene_info *out, uint32_t *out_peer_devices) {
+    if (!m || !out) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_get_info: null argument");
+    *out = m->scenes[0]->info;
+    out->build_ms = m->build_ms;
+    out->upload_ms = m->upload_ms;  // all devices, in parallel
+    if (out_peer_devices) {
+        uint32_t k = 0;
+        for (char p : m->peer) k += p ? 1u : 0u;
+        *out_peer_devices = k;
+    }
+    return RT_OK;
+}
+
+int rt_multi_render(rt_multi *m, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, rt_stats *stats) {
+    if (!m || !out_argb) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_render: null handle or output");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (cfg->tile_world > 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_multi_render: cfg must not use row tiles (the call tiles the frame itself)");
+    const auto t0 = std::chrono::steady_clock::now();
+    const uint32_t n = (uint32_t)m->devices.size(), W = cfg->width, H = cfg->height;
+    const uint32_t tile_rows = cfg->tile_rows ? cfg->tile_rows : 2u;
+    const size_t n_pix = (size_t)W * H;
+    CU_CHECK(cudaSetDevice(m->devices[0]));
+    if ((rc = grow(m->frame, m->frame_cap, n_pix * sizeof(uint32_t)))) return rc;
+    if (m->frame_host_cap < n_pix) {
+        if (m->frame_host) cudaFreeHost(m->frame_host);
+        m->frame_host = nullptr;
+        m->frame_host_cap = 0;
+        CU_CHECK(cudaHostAlloc((void **)&m->frame_host, n_pix * sizeof(uint32_t), cudaHostAllocPortable));
+        m->frame_host_cap = n_pix;
+    }
+    std::vector<int> rcs(n, RT_OK);
+    std::vector<std::string> errs(n);
+    std::vector<rt_config> cfgs(n, *cfg);
+    std::vector<uint64_t> launches(n, 0);
+    m->pool->run([&](int r) {
+        auto body = [&]() -> int {
+            rt_scene *s = m->scenes[r];
+            CU_CHECK(cudaSetDevice(m->devices[r]));
+            int rc2 = check_watchdog(s, false);
+            if (rc2) return rc2;
+            rt_config &c = cfgs[r];
+            if (n > 1) {
+                c.tile_rows = tile_rows;
+                c.tile_rank = (uint32_t)r;
+                c.tile_world = n;
+            } else {
+                c.tile_rows = c.tile_rank = 0;
+                c.tile_world = 1;
+            }
+            RenderParams p;
+            CU_CHECK(cudaEventRecord(s->ev0, s->stream));
+            if (m->peer[r]) {
+                if ((rc2 = enqueue_render(s, &c, p, m->frame, nullptr, s->stream, &launches[r], true))) return rc2;
+            } else {
+                const size_t rows = local_rows_of(&c), bytes = std::max<size_t>(rows * W, 1) * sizeof(uint32_t);
+                if ((rc2 = grow(m->slab[r], m->slab_cap[r], bytes))) return rc2;
+                if (m->slab_host_cap[r] < bytes) {
+                    if (m->slab_host[r]) cudaFreeHost(m->slab_host[r]);
+                    m->slab_host[r] = nullptr;
+                    m->slab_host_cap[r] = 0;
+                    CU_CHECK(cudaHostAlloc((void **)&m->slab_host[r], bytes, cudaHostAllocPortable));
+                    m->slab_host_cap[r] = bytes;
+                }
+                if ((rc2 = enqueue_render(s, &c, p, m->slab[r], nullptr, s->stream, &launches[r], false))) return rc2;
+                if (rows) CU_CHECK(cudaMemcpyAsync(m->slab_host[r], m->slab[r], rows * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            }
+            CU_CHECK(cudaEventRecord(s->ev1, s->stream));
+            if ((rc2 = enqueue_watchdog_fetch(s, s->stream))) return rc2;
+            CU_CHECK(cudaEventRecord(m->done[r], s->stream));
+            return RT_OK;
+        };
+        rcs[r] = body();
+        if (rcs[r]) errs[r] = rt_last_error();
+    });
+    for (uint32_t r = 0; r < n; r++)
+        if (rcs[r]) return rt_fail(rcs[r], "rt_multi_render: device %u: %s", r, errs[r].c_str());
+    // device 0: once every peer has stored its rows, one device-to-host copy of the frame
+    CU_CHECK(cudaSetDevice(m->devices[0]));
+    bool any_peer = false;
+    for (uint32_t r = 0; r < n; r++)
+        if (m->peer[r]) {
+            CU_CHECK(cudaStreamWaitEvent(m->stream0, m->done[r], 0));
+            any_peer = true;
+        }
+    if (any_peer) CU_CHECK(cudaMemcpyAsync(m->frame_host, m->frame, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream0));
+    CU_CHECK(cudaStreamSynchronize(m->stream0));
+    for (uint32_t r = 0; r < n; r++) {
+        CU_CHECK(cudaSetDevice(m->devices[r]));
+        CU_CHECK(cudaEventSynchronize(m->done[r]));
+        if ((rc = check_watchdog(m->scenes[r], true))) return rc;
+    }
+    // ImageBuffer semantics: only hit pixels are stored (pixel != 0 <=> hit, see rt_render)
+    const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
+    auto merge_row = [&](const uint32_t *src, size_t row) {
+        uint32_t *dst = out_argb + row * W;
+        if (zero_misses)
+            memcpy(dst, src, (size_t)W * sizeof(uint32_t));
+        else
+            for (uint32_t x = 0; x < W; x++) dst[x] = src[x] ? src[x] : dst[x];
+        if (out_hit_mask) {
+            uint8_t *dm = out_hit_mask + row * W;
+            for (uint32_t x = 0; x < W; x++) dm[x] = src[x] != 0u;
+        }
+    };
+    for (uint32_t r = 0; r < n; r++) {
+        const uint32_t rows = local_rows_of(&cfgs[r]);
+        for (uint32_t lr = 0; lr < rows; lr++) {
+            const size_t row = image_row_of(&cfgs[r], lr);
+            merge_row(m->peer[r] ? m->frame_host + row * W : m->slab_host[r] + (size_t)lr * W, row);
+        }
+    }
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (uint32_t r = 0; r < n; r++) {
+            CU_CHECK(cudaSetDevice(m->devices[r]));
+            float ms = 0;
+            CU_CHECK(cudaEventElapsedTime(&ms, m->scenes[r]->ev0, m->scenes[r]->ev1));
+            stats->kernel_ms = std::max(stats->kernel_ms, (double)ms);  // max over devices
+            stats->kernel_launches += launches[r];
+            if (cfg->flags & RT_FLAG_COUNT_WORK) {
+                rt_stats st{};
+                if ((rc = fetch_counters(m->scenes[r], &st))) return rc;
+                stats->closest_rays += st.closest_rays;
+                stats->shadow_rays += st.shadow_rays;
+                stats->box_tests += st.box_tests;
+                stats->triangle_tests += st.triangle_tests;
+                stats->sphere_tests += st.sphere_tests;
+                stats->beam_triangle_tests += st.beam_triangle_tests;
+                stats->prepass_box_tests += st.prepass_box_tests;
+                stats->prepass_triangle_tests += st.prepass_triangle_tests;
+                stats->prepass_sphere_tests += st.prepass_sphere_tests;
+            }
+        }
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     return RT_OK;
 }
 

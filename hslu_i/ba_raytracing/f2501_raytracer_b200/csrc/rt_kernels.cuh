@@ -1048,11 +1048,19 @@ __global__ void scale_clouds_kernel(const float *__restrict__ raw, float4 *__res
 }
 
 // antialiased_raytrace's reduction (raytracer_renderer.rs:974-1015) + to_output + ChunkView::set.
-// Writes the rank's compact slab: local row j = image row tile_image_row(j).
-__global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_argb, uint8_t *__restrict__ out_mask) {
+// to_frame == 0: writes the rank's compact slab, local row j = image row tile_image_row(j).
+// to_frame == 1: writes the pixel at its place in a FULL frame (row tile_image_row(j)).  With rt_multi_render that
+// frame lives on device 0 and is reached through NVLink peer memory: the tile gather is these stores, there is no
+// separate collective and no placement pass.
+__global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_argb, uint8_t *__restrict__ out_mask, int to_frame) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n = p.local_rows * p.width;
     if (i >= n) return;
+    size_t o = i;
+    if (to_frame) {
+        const uint32_t lr = i / p.width;
+        o = (size_t)tile_image_row(p, lr) * p.width + (i - lr * p.width);
+    }
     const float4 *s = p.samples + (size_t)i * p.S;
     float3 color;
     bool any = false;
@@ -1083,8 +1091,8 @@ __global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_
             color = (q0 + q2) + (q1 + q3);
         }
     }
-    out_argb[i] = any ? encode_argb(color) : 0u;
-    if (out_mask) out_mask[i] = any ? 1 : 0;
+    out_argb[o] = any ? encode_argb(color) : 0u;
+    if (out_mask) out_mask[o] = any ? 1 : 0;
 }
 
 // debug/parity kernels: raw BVH queries for arbitrary rays

@@ -176,17 +176,59 @@ class DeviceScene:
         return out
 
 
-class RaytracerRenderer:
-    """RaytracerRenderer<C>: `render(buffer, scene)` for a Cargo feature list."""
+class MultiDeviceScene:
+    """rt_multi: the scene replicated on several GPUs of this process; render() splits the frame into interleaved
+    row tiles and every device stores its rows into the first device's frame over NVLink peer memory."""
 
-    def __init__(self, features: str = "", seed: int = 0, device: int = 0):
-        self.features, self.seed, self.device = features, seed, device
+    def __init__(self, flat: FlatScene | Scene, devices: list[int] | None = None, n_devices: int = 0):
+        self._lib = L.load()
+        self.flat = flat.flatten() if isinstance(flat, Scene) else flat
+        h = C.c_void_p()
+        desc = self.flat.desc()
+        arr = None
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            n_devices = len(devices)
+        L.check(self._lib.rt_multi_create(C.byref(desc), arr, n_devices, C.byref(h)))
+        self._h = h
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.rt_multi_destroy(h)
+
+    __del__ = close
+
+    @property
+    def n_devices(self) -> int:
+        return self._lib.rt_multi_device_count(self._h)
+
+    def info(self) -> dict:
+        info, peers = L.SceneInfo(), C.c_uint32(0)
+        L.check(self._lib.rt_multi_get_info(self._h, C.byref(info), C.byref(peers)))
+        d = {k: getattr(info, k) for k, _ in info._fields_}
+        d["peer_devices"] = peers.value
+        return d
+
+    def render(self, rc: RenderConfig, buffer: ImageBuffer | None = None) -> tuple[ImageBuffer, dict]:
+        buf = buffer or ImageBuffer(rc.cfg.width, rc.cfg.height)
+        st = L.Stats()
+        L.check(self._lib.rt_multi_render(self._h, C.byref(rc.cfg), L.ptr(buf.buffer), L.ptr(buf.hit_mask), C.byref(st)))
+        return buf, st.as_dict()
+
+
+class RaytracerRenderer:
+    """RaytracerRenderer<C>: `render(buffer, scene)` for a Cargo feature list.  gpu_count > 1 (or 0 = every visible
+    GPU) partitions the frame inside render(), like the reference's rayon pool does (src/image_buffer.rs:48-97)."""
+
+    def __init__(self, features: str = "", seed: int = 0, device: int = 0, gpu_count: int = 1):
+        self.features, self.seed, self.device, self.gpu_count = features, seed, device, gpu_count
         self.config = RenderConfig.from_features(features, seed)
 
     def render(self, buffer: ImageBuffer, scene: Scene | FlatScene) -> dict:
         if (buffer.width, buffer.height) != (self.config.cfg.width, self.config.cfg.height):
             raise ValueError("ImageBuffer size does not match the feature set's resolution")
-        dev = DeviceScene(scene, self.device)
+        dev = DeviceScene(scene, self.device) if self.gpu_count == 1 else MultiDeviceScene(scene, n_devices=self.gpu_count)
         try:
             _, stats = dev.render(self.config, buffer)
         finally:

@@ -243,6 +243,24 @@ int rt_scatter_tile_rows(const rt_config *cfg_of_rank, const void *d_slab, void 
 int rt_place_tiles(const rt_config *cfg, const void *d_slabs, uint64_t slab_stride_pixels, void *d_frame,
                    void *d_hit_mask, void *cuda_stream);
 
+/* ---- several GPUs, one process (what the Rust shim uses when gpu_count > 1) --------------------------------
+ * The reference partitions the frame inside render() (src/image_buffer.rs:48-97: shuffled chunks on the rayon
+ * pool).  rt_multi_* does the same behind the boundary: the BVH is built once and replicated, the frame is split
+ * into interleaved row tiles (tile t -> device t % N; rt_config.tile_rows, 0 = 2 rows), every device is driven by
+ * its own host thread, and each device's last kernel stores its pixels straight into the frame on the first
+ * device through NVLink peer memory, from where one copy brings the frame to `out_argb`.  No torch, no second
+ * process; `devices` = CUDA device indices (NULL: 0..n-1; n_devices 0: every visible device).  Same image as
+ * rt_render on one device, bit for bit (sampler streams are keyed by pixel).  cfg must not set tile_world. */
+typedef struct rt_multi rt_multi;
+int rt_multi_create(const rt_scene_desc *desc, const int *devices, uint32_t n_devices, rt_multi **out);
+void rt_multi_destroy(rt_multi *m);
+uint32_t rt_multi_device_count(const rt_multi *m);
+/* rt_stats.kernel_ms = the slowest device's kernels; counters are summed over the devices. */
+int rt_multi_render(rt_multi *m, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, rt_stats *stats);
+/* out: the scene as built (build_ms = the one host BVH build, upload_ms = all replicas, in parallel);
+ * out_peer_devices (optional): devices that reach the first device's memory over NVLink / PCIe peer access. */
+int rt_multi_get_info(const rt_multi *m, rt_scene_info *out, uint32_t *out_peer_devices);
+
 /* Debug/parity entry points: raw queries against the device BVH for arbitrary rays
  * (host arrays).  rays: n x 6 floats (origin, un-normalised direction).
  * closest: out_t[n], out_prim[n] (reference primitive index, 0xFFFFFFFF on miss).

@@ -79,6 +79,9 @@ def test_no_cpu_fallback(lib, pkg):
         pkg.RaytracerRenderer("").render(pkg.ImageBuffer(768, 640), flat)
     peak = C.c_double()
     assert lib.rt_measure_fp32_peak(0, C.byref(peak)) == pkg._lib.RT_ERR_NO_DEVICE
+    with pytest.raises(pkg.RtError) as e:
+        pkg.MultiDeviceScene(flat, n_devices=2)  # rt_multi_create: several GPUs in one process -- none here
+    assert e.value.code == pkg._lib.RT_ERR_NO_DEVICE
 
 
 def test_product_never_imports_the_oracle():

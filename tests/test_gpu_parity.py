@@ -355,6 +355,44 @@ def test_device_output_and_scatter(pkg, scenes):
     assert np.array_equal(frame.cpu().numpy().view(np.uint32), host.buffer)
 
 
+@pytest.mark.parametrize("features,kw", [("high_quality,simd_render", dict(width=384, height=320, n_light_clouds=512)),
+                                          ("realistic", dict(width=540, height=450))])
+def test_multi_gpu_in_one_process_behind_the_c_abi(pkg, scenes, features, kw, monkeypatch):
+    """rt_multi_render: N devices driven from one process through the C ABI (no torch): interleaved row tiles, every
+    device's resolve kernel stores into the first device's frame over peer memory.  Same image as rt_render on one
+    device, bit for bit -- with every GPU of the box, with explicit device lists, and on the no-peer fallback."""
+    lib = pkg._lib.load()
+    n_dev = lib.rt_device_count()
+    flat, dev = scenes("semesterbild", features)
+    rc = pkg.RenderConfig.from_features(features, 4, **kw)
+    want, _ = dev.render(rc)
+    rcc = pkg.RenderConfig.from_features(features, 4, extra_flags=pkg._lib.FLAG_COUNT_WORK, **kw)
+    _, st1 = dev.render(rcc)
+    for devices, no_peer in [(None, False), (list(range(n_dev))[::-1], False), ([0], False), (None, True)]:
+        if no_peer:
+            monkeypatch.setenv("RT_MULTI_NO_PEER", "1")
+        multi = pkg.MultiDeviceScene(flat, devices)
+        try:
+            assert multi.n_devices == (n_dev if devices is None else len(devices))
+            info = multi.info()
+            assert info["peer_devices"] == (1 if no_peer else multi.n_devices) and info["n_slots"] >= flat.n_primitives
+            buf = pkg.ImageBuffer(rc.cfg.width, rc.cfg.height)
+            buf.buffer[:] = 0x00ABCDEF
+            got, st = multi.render(rc, buf)
+            miss = want.hit_mask == 0
+            assert np.array_equal(got.hit_mask, want.hit_mask) and np.array_equal(got.buffer[~miss], want.buffer[~miss])
+            assert (got.buffer[miss] == 0x00ABCDEF).all()  # misses stay untouched
+            _, stc = multi.render(rcc)
+            assert (stc["closest_rays"], stc["shadow_rays"]) == (st1["closest_rays"], st1["shadow_rays"])
+            assert st["kernel_ms"] > 0 and st["kernel_launches"] >= 3 * multi.n_devices
+        finally:
+            multi.close()
+    with pytest.raises(pkg.RtError):
+        pkg.MultiDeviceScene(flat, [0, 0])
+    with pytest.raises(pkg.RtError):
+        pkg.MultiDeviceScene(flat, [n_dev])
+
+
 def test_renderer_api_mirror(pkg, oracle_mod):
     """RaytracerRenderer(features).render(buffer, scene): the reference's call shape (src/main.rs:327-334)."""
     scene = pkg.example_scene("test_scene", "backface_culling")
