@@ -7,11 +7,11 @@ there is no CPU, PyTorch or oracle fallback on the product path.
 """
 from . import _lib
 from ._lib import RtError, load
-from .output import FileOutput
+from .output import FileOutput, get_feature_string, window_title
 from .renderer import DeviceScene, ImageBuffer, MultiDeviceScene, RaytracerRenderer, RenderConfig
 from .scene import FlatScene, Mesh, Scene, example_scene, material
 
 __all__ = [
     "DeviceScene", "FileOutput", "FlatScene", "ImageBuffer", "Mesh", "MultiDeviceScene", "RaytracerRenderer", "RenderConfig", "RtError", "Scene",
-    "example_scene", "load", "material",
+    "example_scene", "get_feature_string", "load", "material", "window_title",
 ]

@@ -107,6 +107,7 @@ def _declare(lib: C.CDLL) -> None:
         "rt_last_kernel": (C.c_char_p, [vp]),
         "rt_render": (i32, [vp, P(Config), vp, vp, P(Stats)]),
         "rt_render_progressive": (i32, [vp, P(Config), vp, vp, u32, vp, vp, P(Stats)]),
+        "rt_progressive_overlapped_bands": (u32, [vp]),
         "rt_render_device": (i32, [vp, P(Config), vp, vp, vp, P(Stats)]),
         "rt_frame_constants": (i32, [P(Config), vp, vp, P(u32)]),
         "rt_multi_create": (i32, [P(SceneDesc), vp, u32, P(vp)]),
@@ -140,6 +141,7 @@ def _declare(lib: C.CDLL) -> None:
         "rth_scene_flatten": (i32, [vp, vp, vp, vp, vp]),
         "rth_example_scene": (i32, [C.c_char_p, C.c_char_p, vp, u32, vp, u32, vp, vp, u32, P(vp)]),
         "rth_config_from_features": (i32, [C.c_char_p, P(Config), P(i32), P(i32), P(i32)]),
+        "rth_feature_string": (i32, [C.c_char_p, i32, C.c_char_p, u32]),
         "rth_render": (i32, [vp, C.c_char_p, u64, i32, vp, vp, P(Stats)]),
     }
     for name, (res, args) in sig.items():

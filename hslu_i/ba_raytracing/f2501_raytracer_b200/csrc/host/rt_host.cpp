@@ -74,6 +74,33 @@ bool Features::parse(const std::string &csv, Features &f, std::string &err) {
     return true;
 }
 
+// Output::get_feature_string (reference src/output/mod.rs:25-88): the text the window title carries.  The inner
+// format!("Antialiasing {} {}") is trimmed as a whole (so "ROS_SCL" alone keeps no trailing blank, "RNG" alone no
+// leading one); the depth in the resolution triple is WINDOW_SCENE_DEPTH = (W + H) / 2 (src/lib.rs:74).
+std::string Features::feature_string() const {
+    auto trim = [](std::string t) {
+        const size_t a = t.find_first_not_of(' ');
+        if (a == std::string::npos) return std::string();
+        return t.substr(a, t.find_last_not_of(' ') - a + 1);
+    };
+    std::string out = simd_render ? "SIMD" : "Non-SIMD";
+    out += " | ";
+    if (anti_aliasing)
+        out += trim(std::string("Antialiasing ") + (anti_aliasing_rotation_scale ? "ROS_SCL" : "") + " " + (anti_aliasing_randomness ? "RNG" : ""));
+    else
+        out += "Non-Antialiasing";
+    out += " | ";
+    out += (reflections || refractions) ? (!refractions ? "Reflections" : "Reflections + Refractions") : "Non-Realistic";
+    out += " | ";
+    out += high_quality ? (extreme_quality ? "Extreme Quality" : "High Quality") : "Standard Quality";
+    out += " | ";
+    out += high_resolution ? "High Resolution" : (medium_resolution ? "Medium Resolution" : "Small Resolution");
+    const uint32_t W = window_width(), H = window_height();
+    out += " (" + std::to_string(W) + "\xC3\x97" + std::to_string(H) + "\xC3\x97" + std::to_string((W + H) / 2) + ") | ";  // U+00D7
+    out += backface_culling ? "Backface Culling" : "NO-OPT";
+    return trim(out);
+}
+
 uint32_t Features::render_flags() const {
     uint32_t fl = 0;
     if (anti_aliasing) fl |= RT_FLAG_ANTI_ALIASING;
@@ -755,6 +782,17 @@ int rth_config_from_features(const char *features_csv, rt_config *cfg, int *high
     if (high_quality_model) *high_quality_model = (f.high_quality_model || f.medium_resolution) ? 1 : 0;  // src/main.rs:31-35
     if (scene_backface_culling) *scene_backface_culling = f.scene_backface_culling ? 1 : 0;
     if (anti_aliasing_randomness) *anti_aliasing_randomness = f.anti_aliasing_randomness ? 1 : 0;
+    return RT_OK;
+}
+
+int rth_feature_string(const char *features_csv, int with_title_prefix, char *out, uint32_t out_size) {
+    if (!out || out_size == 0) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rth_feature_string: null output");
+    rth::Features f;
+    std::string err;
+    if (!rth::Features::parse(features_csv ? features_csv : "", f, err)) return rt_fail(RT_ERR_INVALID_ARGUMENT, "%s", err.c_str());
+    const std::string t = with_title_prefix ? f.window_title() : f.feature_string();
+    if (t.size() + 1 > out_size) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rth_feature_string: buffer of %u bytes is too small (%zu needed)", out_size, t.size() + 1);
+    memcpy(out, t.c_str(), t.size() + 1);
     return RT_OK;
 }
 

@@ -120,6 +120,9 @@ struct Features {
     }
     uint32_t antialiasing_samples_per_pixel() const { return extreme_quality ? 24 : 9; }
     uint32_t render_flags() const;
+    // Output::get_feature_string (src/output/mod.rs:25-88) and the window title built from it (src/output/window.rs:58-64)
+    std::string feature_string() const;
+    std::string window_title() const { return "Raytracer - " + feature_string(); }
 };
 
 // ---------------------------------------------------------------- materials & geometry

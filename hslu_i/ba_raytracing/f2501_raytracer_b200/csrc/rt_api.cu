@@ -82,6 +82,14 @@ struct rt_scene {
     static constexpr uint32_t KERNEL_EVENT_RING = 64;
     cudaEvent_t kev[KERNEL_EVENT_RING][2] = {};
     uint64_t kev_count = 0;
+    // rt_render_progressive: two-deep band pipeline
+    uint32_t *band_slab[2] = {nullptr, nullptr};
+    size_t band_slab_cap[2] = {0, 0};
+    uint32_t *band_host[2] = {nullptr, nullptr};
+    size_t band_host_cap[2] = {0, 0};
+    cudaEvent_t band_rendered[2] = {nullptr, nullptr}, band_copied[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    uint32_t last_progressive_overlapped = 0;
     char last_kernel[64] = "";
     rt_scene_info info{};
 };
@@ -659,6 +667,13 @@ void rt_scene_destroy(rt_scene *s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_watchdog) cudaEventDestroy(s->ev_watchdog);
     if (s->ev_last) cudaEventDestroy(s->ev_last);
+    for (int k = 0; k < 2; k++) {
+        if (s->band_slab[k]) cudaFree(s->band_slab[k]);
+        if (s->band_host[k]) cudaFreeHost(s->band_host[k]);
+        if (s->band_rendered[k]) cudaEventDestroy(s->band_rendered[k]);
+        if (s->band_copied[k]) cudaEventDestroy(s->band_copied[k]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     for (auto &pair : s->kev)
         for (cudaEvent_t e : pair)
             if (e) cudaEventDestroy(e);
@@ -773,14 +788,10 @@ int rt_render(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *ou
     return RT_OK;
 }
 
-int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, uint32_t band_rows, rt_band_callback on_band,
-                          void *user, rt_stats *stats) {
-    if (!s || !out_argb || band_rows == 0) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: null scene / output or band_rows == 0");
-    int rc = validate_config(cfg);
-    if (rc) return rc;
-    if (cfg->tile_world > 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: cfg must not use row tiles");
-    // a band = one row tile: tile b of `n_bands` tiles of band_rows rows, owned by "rank" b
-    const uint32_t n_bands = (cfg->height + band_rows - 1) / band_rows;
+// one band of a progressive render, serial form: render, copy, merge, in order (the counter build uses it: the
+// device counters are per call)
+static int progressive_serial(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, uint32_t band_rows, uint32_t n_bands,
+                              rt_band_callback on_band, void *user, rt_stats *stats) {
     rt_stats total;
     memset(&total, 0, sizeof(total));
     for (uint32_t b = 0; b < n_bands; b++) {
@@ -789,7 +800,8 @@ int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb,
         band.tile_rank = b;
         band.tile_world = n_bands;
         rt_stats st;
-        if ((rc = rt_render(s, &band, out_argb, out_hit_mask, &st))) return rc;
+        int rc = rt_render(s, &band, out_argb, out_hit_mask, &st);
+        if (rc) return rc;
         total.kernel_ms += st.kernel_ms;
         total.total_ms += st.total_ms;
         total.closest_rays += st.closest_rays;
@@ -808,6 +820,100 @@ int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb,
     if (stats) *stats = total;
     return RT_OK;
 }
+
+// The reference's window re-blits the shared ImageBuffer at 60 fps while the render thread fills it
+// (src/output/window.rs:73-84, src/main.rs:342-347).  Here the frame is rendered in horizontal bands with a
+// two-deep pipeline: band k+1 is rendering on the scene's stream while band k's pixels travel device-to-host on a
+// copy stream (two device slabs, two pinned buffers) and the host merges band k into the caller's buffer and runs
+// the callback.  The GPU never waits for the host: the next band is enqueued before the host blocks on band k's copy.
+int rt_render_progressive(rt_scene *s, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask, uint32_t band_rows, rt_band_callback on_band,
+                          void *user, rt_stats *stats) {
+    if (!s || !out_argb || band_rows == 0) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: null scene / output or band_rows == 0");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (cfg->tile_world > 1) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_render_progressive: cfg must not use row tiles");
+    // a band = one row tile: tile b of `n_bands` tiles of band_rows rows, owned by "rank" b
+    const uint32_t n_bands = (cfg->height + band_rows - 1) / band_rows, W = cfg->width;
+    if (cfg->flags & RT_FLAG_COUNT_WORK) return progressive_serial(s, cfg, out_argb, out_hit_mask, band_rows, n_bands, on_band, user, stats);
+    CU_CHECK(cudaSetDevice(s->device));
+    if ((rc = check_watchdog(s, false))) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t band_pix = (size_t)std::min(band_rows, cfg->height) * W;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = grow(s->band_slab[k], s->band_slab_cap[k], band_pix * sizeof(uint32_t)))) return rc;
+        if (s->band_host_cap[k] < band_pix) {
+            if (s->band_host[k]) cudaFreeHost(s->band_host[k]);
+            s->band_host[k] = nullptr;
+            s->band_host_cap[k] = 0;
+            CU_CHECK(cudaMallocHost((void **)&s->band_host[k], band_pix * sizeof(uint32_t)));
+            s->band_host_cap[k] = band_pix;
+        }
+        if (!s->band_rendered[k]) CU_CHECK(cudaEventCreateWithFlags(&s->band_rendered[k], cudaEventDisableTiming));
+        if (!s->band_copied[k]) CU_CHECK(cudaEventCreateWithFlags(&s->band_copied[k], cudaEventDisableTiming));
+    }
+    if (!s->copy_stream) CU_CHECK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
+    uint64_t launches = 0;
+    uint32_t overlapped = 0;  // bands whose successor was still rendering when their host merge began
+    auto enqueue_band = [&](uint32_t b) -> int {
+        rt_config band = *cfg;
+        band.tile_rows = band_rows;
+        band.tile_rank = b;
+        band.tile_world = n_bands;
+        const int k = (int)(b & 1u);
+        // slab k was last read by the copy of band b - 2
+        if (b >= 2) CU_CHECK(cudaStreamWaitEvent(s->stream, s->band_copied[k], 0));
+        RenderParams p;
+        int rc2 = enqueue_render(s, &band, p, s->band_slab[k], nullptr, s->stream, &launches);
+        if (rc2) return rc2;
+        CU_CHECK(cudaEventRecord(s->band_rendered[k], s->stream));
+        CU_CHECK(cudaStreamWaitEvent(s->copy_stream, s->band_rendered[k], 0));
+        const uint32_t first = b * band_rows, n_rows = std::min(band_rows, cfg->height - first);
+        CU_CHECK(cudaMemcpyAsync(s->band_host[k], s->band_slab[k], (size_t)n_rows * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
+        CU_CHECK(cudaEventRecord(s->band_copied[k], s->copy_stream));
+        return RT_OK;
+    };
+    CU_CHECK(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = enqueue_band(0))) return rc;
+    bool stopped = false;
+    for (uint32_t b = 0; b < n_bands && !stopped; b++) {
+        if (b + 1 < n_bands && (rc = enqueue_band(b + 1))) return rc;  // keep the GPU busy before blocking on band b
+        const int k = (int)(b & 1u);
+        CU_CHECK(cudaEventSynchronize(s->band_copied[k]));
+        if (b + 1 < n_bands && cudaEventQuery(s->band_rendered[(b + 1) & 1u]) == cudaErrorNotReady) overlapped++;
+        const uint32_t first = b * band_rows, n_rows = std::min(band_rows, cfg->height - first);
+        for (uint32_t r = 0; r < n_rows; r++) {
+            const uint32_t *src = s->band_host[k] + (size_t)r * W;
+            uint32_t *dst = out_argb + (size_t)(first + r) * W;
+            if (zero_misses)
+                memcpy(dst, src, (size_t)W * sizeof(uint32_t));
+            else
+                for (uint32_t x = 0; x < W; x++) dst[x] = src[x] ? src[x] : dst[x];
+            if (out_hit_mask) {
+                uint8_t *dm = out_hit_mask + (size_t)(first + r) * W;
+                for (uint32_t x = 0; x < W; x++) dm[x] = src[x] != 0u;
+            }
+        }
+        if (on_band && on_band(user, first, n_rows)) stopped = true;  // (a band already in flight finishes; its rows stay untouched)
+    }
+    CU_CHECK(cudaEventRecord(s->ev1, s->stream));
+    if ((rc = enqueue_watchdog_fetch(s, s->stream))) return rc;
+    CU_CHECK(cudaStreamSynchronize(s->stream));
+    CU_CHECK(cudaStreamSynchronize(s->copy_stream));
+    if ((rc = check_watchdog(s, true))) return rc;
+    s->last_progressive_overlapped = overlapped;
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        float ms = 0;
+        CU_CHECK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        stats->kernel_ms = ms;
+        stats->kernel_launches = launches;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+    return RT_OK;
+}
+
+uint32_t rt_progressive_overlapped_bands(const rt_scene *s) { return s ? s->last_progressive_overlapped : 0; }
 
 int rt_frame_constants(const rt_config *cfg, float *out_constants, float *out_offsets, uint32_t *out_samples) {
     int rc = validate_config(cfg);

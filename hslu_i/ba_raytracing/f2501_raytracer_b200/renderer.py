@@ -131,7 +131,9 @@ class DeviceScene:
         st = L.Stats()
         cb = L.BAND_CALLBACK(lambda _user, first, n: 1 if (on_band and on_band(first, n)) else 0)
         L.check(self._lib.rt_render_progressive(self._h, C.byref(rc.cfg), L.ptr(buf.buffer), L.ptr(buf.hit_mask), band_rows, cb, None, C.byref(st)))
-        return buf, st.as_dict()
+        d = st.as_dict()
+        d["overlapped_bands"] = self._lib.rt_progressive_overlapped_bands(self._h)
+        return buf, d
 
     def render_device(self, rc: RenderConfig, d_argb: int, d_mask: int | None, stream: int | None = None,
                       want_stats: bool = False) -> dict | None:

@@ -202,9 +202,16 @@ int rt_render(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t
  * (src/output/window.rs:73-84, src/main.rs:342-347).  A non-zero return value of the callback stops the render
  * (rt_render_progressive then returns RT_OK; the remaining rows are untouched).  `cfg` must not use row tiles.
  * The image is exactly rt_render's.  `stats` (optional) sums the bands. */
+/* Pipeline: while band k's pixels travel device-to-host on a copy stream and the host merges them and runs the
+ * callback, band k+1 is already rendering (two device slabs, two pinned buffers), so the callback's work hides
+ * behind the GPU like the reference's window loop hides behind its render thread.  The callback runs on the
+ * calling thread.  rt_progressive_overlapped_bands: in the last progressive call on this scene, the number of
+ * bands whose successor was still rendering when their merge began (measurement only). */
 typedef int (*rt_band_callback)(void *user, uint32_t first_row, uint32_t n_rows);
 int rt_render_progressive(rt_scene *scene, const rt_config *cfg, uint32_t *out_argb, uint8_t *out_hit_mask,
                           uint32_t band_rows, rt_band_callback on_band, void *user, rt_stats *stats);
+
+uint32_t rt_progressive_overlapped_bands(const rt_scene *scene);
 
 /* Same, but the outputs are DEVICE pointers and the work is enqueued on `cuda_stream`
  * (a cudaStream_t; NULL is the legacy default stream).  With row tiles the output is the rank's COMPACT slab:

@@ -62,6 +62,12 @@ int rth_example_scene(const char *name, const char *features_csv, const float *p
 int rth_config_from_features(const char *features_csv, rt_config *cfg, int *high_quality_model, int *scene_backface_culling,
                              int *anti_aliasing_randomness);
 
+/* Output::get_feature_string() for a feature list (src/output/mod.rs:25-88), e.g.
+ * "SIMD | Antialiasing ROS_SCL RNG | Reflections + Refractions | High Quality | Medium Resolution (1140x950x1045) | NO-OPT"
+ * (with U+00D7 multiplication signs, UTF-8); with_title_prefix != 0: the window title "Raytracer - ..." the
+ * reference sets (src/output/window.rs:58-64).  NUL-terminated into out[out_size]. */
+int rth_feature_string(const char *features_csv, int with_title_prefix, char *out, uint32_t out_size);
+
 /* RaytracerRenderer::render(&buffer, &scene) for a feature list: flatten, rt_scene_create on `device`,
  * sampler tables from `seed`, rt_render into out_argb (width*height of the feature set). */
 int rth_render(const rth_scene *s, const char *features_csv, uint64_t seed, int device, uint32_t *out_argb,

@@ -193,3 +193,37 @@ def test_file_output_writes_the_framebuffer_as_rgb8_png(pkg, tmp_path):
     img = PIL.open(out)
     assert img.mode == "RGB" and img.size == (7, 5)
     assert np.array_equal(np.asarray(img), buf.rgb())
+
+
+def test_feature_string_and_window_title(pkg, tmp_path):
+    """Output::get_feature_string (reference src/output/mod.rs:25-88) and the window title built from it
+    (src/output/window.rs:58-64): expected strings written out by hand from the format! call."""
+    X = "×"
+    cases = {
+        "": f"Non-SIMD | Non-Antialiasing | Non-Realistic | Standard Quality | Small Resolution (768{X}640{X}704) | NO-OPT",
+        "default,simd_render": f"SIMD | Antialiasing ROS_SCL RNG | Reflections + Refractions | High Quality | Medium Resolution (1140{X}950{X}1045) | NO-OPT",
+        "simd_render,backface_culling,medium_resolution": f"SIMD | Non-Antialiasing | Non-Realistic | Standard Quality | Medium Resolution (1140{X}950{X}1045) | Backface Culling",
+        "high_quality": f"Non-SIMD | Antialiasing | Non-Realistic | High Quality | Small Resolution (768{X}640{X}704) | NO-OPT",
+        "extreme_quality,realistic,high_resolution,simd_render": f"SIMD | Antialiasing | Reflections + Refractions | Extreme Quality | High Resolution (1620{X}1350{X}1485) | NO-OPT",
+        "reflections": f"Non-SIMD | Non-Antialiasing | Reflections | Standard Quality | Small Resolution (768{X}640{X}704) | NO-OPT",
+        # format!("Antialiasing {} {}", "", "RNG").trim() keeps the inner double blank; "ROS_SCL" alone loses its trailing one
+        "anti_aliasing_randomness": f"Non-SIMD | Antialiasing  RNG | Non-Realistic | Standard Quality | Small Resolution (768{X}640{X}704) | NO-OPT",
+        "anti_aliasing_rotation_scale": f"Non-SIMD | Antialiasing ROS_SCL | Non-Realistic | Standard Quality | Small Resolution (768{X}640{X}704) | NO-OPT",
+    }
+    for feat, want in cases.items():
+        assert pkg.get_feature_string(feat) == want
+        assert pkg.window_title(feat) == "Raytracer - " + want
+    with pytest.raises(pkg.RtError):
+        pkg.get_feature_string("no_such_feature")
+    # FileOutput(path, features=...): the title travels in a tEXt chunk; the pixels are the same file without it
+    buf = pkg.ImageBuffer(16, 8)
+    buf.buffer[::3] = 0xFF336699
+    a, b = tmp_path / "plain.png", tmp_path / "titled.png"
+    pkg.FileOutput(a).render_buffer(buf)
+    pkg.FileOutput(b, features="default,simd_render").render_buffer(buf)
+    raw_a, raw_b = a.read_bytes(), b.read_bytes()
+    title = ("Raytracer - " + cases["default,simd_render"]).encode("latin-1")
+    assert b"tEXt" not in raw_a and b"tEXtTitle\x00" + title in raw_b
+    i = raw_b.index(b"tEXt") - 4
+    n = int.from_bytes(raw_b[i:i + 4], "big")
+    assert raw_b[:i] + raw_b[i + 12 + n:] == raw_a
