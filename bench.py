@@ -284,6 +284,31 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, headline: bool) -> dic
     dev = DeviceScene(flat, device=ctx.local_rank)  # rt_scene_create: BVH build + upload
     torch.cuda.synchronize()
     scene_create_ms = ctx.allmax(1e3 * (time.perf_counter() - t0))
+    bvh_info = dev.bvh_info()
+    host_builder = None
+    if bvh_info["builder"] == 1 and not headline:
+        # the scene was built on the GPU: for comparison, the host builder's time and the frame time on ITS tree
+        os.environ["RT_BVH_BUILDER"] = "host"
+        try:
+            t0 = time.perf_counter()
+            dev_h = DeviceScene(flat, device=ctx.local_rank)
+            torch.cuda.synchronize()
+            create_h = ctx.allmax(1e3 * (time.perf_counter() - t0))
+            th = TiledRenderer(dev_h, rc, rank, world, args.tile_rows)
+            th.step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.barrier()
+            e0.record()
+            th.step()
+            e1.record()
+            torch.cuda.synchronize()
+            th.check()
+            host_builder = {"scene_create_ms": create_h, "ms_per_frame": ctx.allmax(e0.elapsed_time(e1)), "bvh": dev_h.bvh_info()}
+            dev_h.close()
+            del th
+        finally:
+            del os.environ["RT_BVH_BUILDER"]
     tiled = TiledRenderer(dev, rc, rank, world, args.tile_rows)
 
     # ---- untimed: work counters of this rank's tiles (counter build of the same kernels)
@@ -379,12 +404,12 @@ def measure(ctx: Ctx, name: str, steps: int, warmup: int, headline: bool) -> dic
     e2e_ms = 1e3 * e2e_s / steps
 
     bounces = bool(rc.cfg.flags & (L.FLAG_REFLECTIONS | L.FLAG_REFRACTIONS))
-    dominant_kernel = dev.dominant_kernel_name() if hasattr(dev, "dominant_kernel_name") else ("render_kernel" if bounces else "direct_kernel")
+    dominant_kernel = dev.dominant_kernel_name()
     res = dict(name=name, flat=flat, rc=rc, features=features, desc=desc, counts=counts, counts_ray=counts_ray, rays_per_frame=rays_per_frame,
                flops_alg=flops_alg, bytes_alg=bytes_alg, flops_ray=flops_ray, kernel_ms=dom_ms_max, render_ms=kern_ms_max / steps,
                ms_per_step=ms_per_step, e2e_ms=e2e_ms, h2d=h2d, d2h=d2h, clocks=clocks, wall=wall, scene_create_ms=scene_create_ms,
                host_scene_s=host_scene_s, dominant_kernel=dominant_kernel, steps=steps, warmup=warmup,
-               launches_per_step=int(counts["kernel_launches"]) + (0 if world == 1 else 1), bvh=dev.bvh_info() if hasattr(dev, "bvh_info") else None)
+               launches_per_step=int(counts["kernel_launches"]) + (0 if world == 1 else 1), bvh=bvh_info, host_builder=host_builder)
     dev.close()
     del tiled
     torch.cuda.empty_cache()
@@ -427,6 +452,7 @@ def main() -> None:
             "roofline_frac_fp32": ach / ctx.fp32_peak if ach and ctx.fp32_peak else None, "achieved_tflops": ach,
             "algorithmic_gbs": s["bytes_alg"] / world / (s["kernel_ms"] * 1e-3) / 1e9 if s["kernel_ms"] else None,
             "scene_create_ms": s["scene_create_ms"], "primitives": s["flat"].n_primitives, "bvh": s["bvh"],
+            "host_builder_for_comparison": s["host_builder"],
             "tests_per_ray": {k2: s["counts"][k2] / s["rays_per_frame"] for k2 in ("box_tests", "triangle_tests", "sphere_tests", "beam_triangle_tests")},
         }
 

@@ -19,8 +19,8 @@ ROOT = PKG.parents[2]
 CSRC = PKG / "csrc"
 OUT = Path(os.environ.get("RT_LIB_PATH", PKG / "librt_b200.so"))  # RT_LIB_PATH / RT_NVCC_EXTRA: tuning experiments only
 
-SOURCES = [CSRC / "rt_api.cu", CSRC / "rt_bvh.cpp", CSRC / "rt_sampler.cpp", CSRC / "rt_error.cpp", CSRC / "host" / "rt_host.cpp"]
-HEADERS = [CSRC / "rt_device.cuh", CSRC / "rt_kernels.cuh", CSRC / "rt_bvh.h", CSRC / "rt_internal.h", CSRC / "host" / "rt_host.hpp",
+SOURCES = [CSRC / "rt_api.cu", CSRC / "rt_bvh_device.cu", CSRC / "rt_bvh.cpp", CSRC / "rt_sampler.cpp", CSRC / "rt_error.cpp", CSRC / "host" / "rt_host.cpp"]
+HEADERS = [CSRC / "rt_device.cuh", CSRC / "rt_kernels.cuh", CSRC / "rt_bvh.h", CSRC / "rt_bvh_device.h", CSRC / "rt_internal.h", CSRC / "host" / "rt_host.hpp",
            ROOT / "include" / "rt_api.h", ROOT / "include" / "rt_host.h"]
 
 NVCC_FLAGS = [

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "rt_bvh.h"
+#include "rt_bvh_device.h"
 #include "rt_internal.h"
 #include "rt_kernels.cuh"
 
@@ -519,6 +520,9 @@ struct DevBufs {  // frees its device buffers on every exit path
 }  // namespace
 
 static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_ms, rt_scene **out_scene);
+static int scene_from_device_build(const rt_scene_desc *desc, int device, rt_scene **out_scene);
+static bool use_device_builder(const rt_scene_desc *desc);
+constexpr int RT_BUILD_FALLBACK = 1;  // scene_from_device_build: use the host builder instead
 
 extern "C" {
 
@@ -581,15 +585,95 @@ int rt_device_count(void) {
 int rt_scene_create(const rt_scene_desc *desc, int device, rt_scene **out_scene) {
     if (!out_scene) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null out_scene");
     *out_scene = nullptr;
+    int rc = rtb::check_scene_desc(desc);
+    if (rc) return rc;
+    if (use_device_builder(desc)) {
+        rc = scene_from_device_build(desc, device, out_scene);
+        if (rc != RT_BUILD_FALLBACK) return rc;  // (tree too deep for the traversal stack: the host builder bounds its depth)
+    }
     rtb::FlatScene flat;
     const auto t_build0 = std::chrono::steady_clock::now();
-    int rc = rtb::build_flat_scene(desc, flat);
+    rc = rtb::build_flat_scene(desc, flat);
     if (rc) return rc;
     const double build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
     return scene_from_flat(flat, device, build_ms, out_scene);
 }
 
 }  // extern "C"
+
+// Which builder: the host's binned-SAH build gives the better tree and costs milliseconds for the reference's own
+// scenes (14.6 k primitives); from DEVICE_BUILD_MIN primitives on the build runs on the GPU (rt_bvh_device.cu).
+// RT_BVH_BUILDER=host|device overrides (A/B runs, tests).
+constexpr uint32_t DEVICE_BUILD_MIN = 1u << 17;
+static bool use_device_builder(const rt_scene_desc *desc) {
+    const uint64_t n = (uint64_t)desc->n_triangles + desc->n_spheres;
+    if (const char *e = getenv("RT_BVH_BUILDER")) {
+        if (!strcmp(e, "host")) return false;
+        if (!strcmp(e, "device")) return n >= 16;
+    }
+    return n >= DEVICE_BUILD_MIN;
+}
+
+static int scene_finish(rt_scene *s);
+
+static int scene_from_device_build(const rt_scene_desc *desc, int device, rt_scene **out_scene) {
+    *out_scene = nullptr;
+    int rc = select_device(device);
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    rtb::FlatScene small;  // materials and lights only
+    std::vector<uint8_t> transmissive;
+    rtb::pack_materials_and_lights(desc, small, transmissive);
+    rtb::DeviceBvh bvh;
+    if ((rc = rtb::build_scene_on_device(desc, transmissive, bvh))) return rc;
+    constexpr uint32_t MAX_BVH4_DEPTH = 20;  // the traversal stack holds 3 * depth + 1 references (rt_device.cuh, rt_bvh.cpp)
+    if (bvh.max_depth > MAX_BVH4_DEPTH) {
+        cudaFree(bvh.nodes);
+        cudaFree(bvh.prims);
+        cudaFree(bvh.shade_n);
+        return RT_BUILD_FALLBACK;
+    }
+    rt_scene *s = new (std::nothrow) rt_scene();
+    if (!s) {
+        cudaFree(bvh.nodes);
+        cudaFree(bvh.prims);
+        cudaFree(bvh.shade_n);
+        return rt_fail(RT_ERR_OUT_OF_MEMORY, "out of host memory");
+    }
+    s->device = device;
+    s->buf_nodes = bvh.nodes;
+    s->buf_prims = bvh.prims;
+    s->buf_shade = bvh.shade_n;
+    auto fail = [&](int code) {
+        rt_scene_destroy(s);
+        return code;
+    };
+    if ((rc = upload(&s->buf_mats, small.mats))) return fail(rc);
+    if ((rc = upload(&s->buf_lights, small.lights))) return fail(rc);
+    s->d.nodes = (const float4 *)s->buf_nodes;
+    s->d.prims = (const float4 *)s->buf_prims;
+    s->d.shade_n = (const float4 *)s->buf_shade;
+    s->d.mats = (const float4 *)s->buf_mats;
+    s->d.lights = (const float4 *)s->buf_lights;
+    s->d.n_prims = bvh.n_slots;
+    s->d.n_lights = desc->n_lights;
+    s->d.nan_hit_slot = bvh.nan_hit_slot;
+    s->d.nan_hit_slot_culled = bvh.nan_hit_slot_culled;
+    s->d.box_pad = bvh.box_pad;
+    s->n_nodes = bvh.n_nodes;
+    s->n_prims = bvh.n_slots;
+    s->info.n_nodes = bvh.n_nodes;
+    s->info.n_slots = bvh.n_slots;
+    s->info.bvh_depth = bvh.max_depth;
+    s->info.builder = 1;
+    CU_CHECK(cudaDeviceSynchronize());
+    s->info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();  // incl. the upload of the primitives
+    s->info.upload_ms = 0.0;
+    s->info.device_bytes = (uint64_t)bvh.n_nodes * 128 + (uint64_t)bvh.n_slots * 80 + (small.mats.size() + small.lights.size()) * sizeof(float);
+    if ((rc = scene_finish(s))) return fail(rc);
+    *out_scene = s;
+    return RT_OK;
+}
 
 // uploads a flattened scene to `device` and allocates the per-scene scratch (the second half of rt_scene_create;
 // rt_multi_create builds the BVH once and runs this once per device)
@@ -629,11 +713,18 @@ static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_
     s->info.build_ms = build_ms;
     s->info.upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build1).count();
     s->info.device_bytes = (flat.nodes.size() + flat.prims.size() + flat.shade_n.size() + flat.mats.size() + flat.lights.size()) * sizeof(float);
+    if ((rc = scene_finish(s))) return fail(rc);
+    *out_scene = s;
+    return RT_OK;
+}
+
+// occupancy of the render kernels on this device + the per-scene scratch every render call uses
+static int scene_finish(rt_scene *s) {
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(rt_fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) return rt_fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed");
     s->sm_count = prop.multiProcessorCount;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm, render_kernel<false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm < 1)
-        return fail(rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError())));
+        return rt_fail(RT_ERR_CUDA, "render kernel cannot be launched on this device (built for sm_100a): %s", cudaGetErrorString(cudaGetLastError()));
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_count, render_kernel<true>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_count < 1)
         s->ctas_per_sm_count = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->ctas_per_sm_direct, direct_kernel<false, true, false>, CTA_THREADS, 0) != cudaSuccess || s->ctas_per_sm_direct < 1)
@@ -646,8 +737,7 @@ static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_
         cudaMemset(s->d_watchdog, 0, sizeof(unsigned int)) != cudaSuccess || cudaMallocHost((void **)&s->h_watchdog, sizeof(unsigned int)) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_watchdog, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_last, cudaEventDisableTiming) != cudaSuccess)
-        return fail(rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError())));
-    *out_scene = s;
+        return rt_fail(RT_ERR_CUDA, "scene scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return RT_OK;
 }
 
@@ -1136,15 +1226,28 @@ int rt_multi_create(const rt_scene_desc *desc, const int *devices, uint32_t n_de
             }
         m->devices.push_back(d);
     }
-    // the BVH is built once, on the host, and uploaded to every device by its own worker thread
-    rtb::FlatScene flat;
-    const auto t0 = std::chrono::steady_clock::now();
-    int rc = rtb::build_flat_scene(desc, flat);
+    // Small scenes: the BVH is built once, on the host, and uploaded to every device by its own worker thread.
+    // Large scenes: every device builds its own copy (rt_bvh_device.cu; deterministic, so the replicas are identical).
+    int rc = rtb::check_scene_desc(desc);
     if (rc) {
         multi_free(m);
         return rc;
     }
-    m->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    const bool device_build = use_device_builder(desc);
+    rtb::FlatScene flat;
+    bool have_flat = false;
+    auto host_build = [&]() -> int {
+        if (have_flat) return RT_OK;
+        const auto t0 = std::chrono::steady_clock::now();
+        const int rc2 = rtb::build_flat_scene(desc, flat);
+        m->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        have_flat = rc2 == RT_OK;
+        return rc2;
+    };
+    if (!device_build && (rc = host_build())) {
+        multi_free(m);
+        return rc;
+    }
     const uint32_t n = n_devices;
     m->scenes.assign(n, nullptr);
     m->peer.assign(n, 0);
@@ -1157,8 +1260,12 @@ int rt_multi_create(const rt_scene_desc *desc, const int *devices, uint32_t n_de
     std::vector<int> rcs(n, RT_OK);
     std::vector<std::string> errs(n);
     const auto t1 = std::chrono::steady_clock::now();
-    m->pool->run([&](int r) {
-        int rc2 = scene_from_flat(flat, m->devices[r], m->build_ms, &m->scenes[r]);
+    auto create_on = [&](int r, bool from_flat) {
+        int rc2 = from_flat ? scene_from_flat(flat, m->devices[r], m->build_ms, &m->scenes[r]) : scene_from_device_build(desc, m->devices[r], &m->scenes[r]);
+        if (rc2 == RT_BUILD_FALLBACK) {  // tree too deep for the traversal stack: host build below
+            rcs[r] = RT_BUILD_FALLBACK;
+            return;
+        }
         if (!rc2 && cudaEventCreateWithFlags(&m->done[r], cudaEventDisableTiming) != cudaSuccess) rc2 = rt_fail(RT_ERR_CUDA, "cudaEventCreate failed");
         if (!rc2) {
             if (r == 0) {
@@ -1175,7 +1282,20 @@ int rt_multi_create(const rt_scene_desc *desc, const int *devices, uint32_t n_de
         }
         rcs[r] = rc2;
         if (rc2) errs[r] = rt_last_error();
-    });
+    };
+    m->pool->run([&](int r) { create_on(r, !device_build); });
+    bool fallback = false;
+    for (uint32_t r = 0; r < n; r++) fallback |= rcs[r] == RT_BUILD_FALLBACK;
+    if (fallback) {
+        if ((rc = host_build())) {
+            multi_free(m);
+            return rc;
+        }
+        m->pool->run([&](int r) {
+            if (rcs[r] == RT_BUILD_FALLBACK) create_on(r, true);
+        });
+    }
+    if (device_build && !fallback && m->scenes[0]) m->build_ms = m->scenes[0]->info.build_ms;
     m->upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
     for (uint32_t r = 0; r < n; r++)
         if (rcs[r]) {

@@ -269,7 +269,7 @@ inline float u2f(uint32_t u) {
 
 }  // namespace
 
-int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
+int check_scene_desc(const rt_scene_desc *d) {
     if (!d) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: null scene description");
     if ((d->n_triangles && !d->triangles) || (d->n_spheres && !d->spheres) || (d->n_materials && !d->materials) ||
         (d->n_lights && !d->lights))
@@ -277,26 +277,14 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
     const uint64_t n64 = (uint64_t)d->n_triangles + d->n_spheres;
     if (n64 > LEAF_FIRST_MASK) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: too many primitives (%llu)", (unsigned long long)n64);
     if (d->n_materials > PRIM_MATERIAL_MASK) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_create: too many materials");
-    const uint32_t n = (uint32_t)n64, ns = d->n_spheres, nt = d->n_triangles;
-    for (uint32_t i = 0; i < ns; i++)
-        if (d->spheres[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "sphere %u: material index out of range", i);
-    for (uint32_t i = 0; i < nt; i++)
-        if (d->triangles[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u: material index out of range", i);
+    return RT_OK;
+}
 
-    const bool verbose = getenv("RT_BVH_VERBOSE") != nullptr;  // stage timings on stderr (tuning)
-    auto t_last = std::chrono::steady_clock::now();
-    auto stage = [&](const char *name) {
-        if (!verbose) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[rt_bvh] %-28s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
-        t_last = now;
-    };
-    out = FlatScene();
+// materials (48 B each) and lights (32 B each) in their device layout; transmissive[m] = TransmissionProperties::mask
+void pack_materials_and_lights(const rt_scene_desc *d, FlatScene &out, std::vector<uint8_t> &transmissive) {
     out.n_mats = d->n_materials;
     out.n_lights = d->n_lights;
-
-    // materials and lights
-    std::vector<uint8_t> transmissive(d->n_materials);
+    transmissive.assign(d->n_materials, 0);
     out.mats.resize(12 * (size_t)d->n_materials);
     for (uint32_t i = 0; i < d->n_materials; i++) {
         const rt_material &m = d->materials[i];
@@ -315,6 +303,27 @@ int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
         o[0] = l.position[0]; o[1] = l.position[1]; o[2] = l.position[2]; o[3] = l.intensity;
         o[4] = l.color[0]; o[5] = l.color[1]; o[6] = l.color[2]; o[7] = 0;
     }
+}
+
+int build_flat_scene(const rt_scene_desc *d, FlatScene &out) {
+    if (int rc = check_scene_desc(d)) return rc;
+    const uint32_t n = d->n_triangles + d->n_spheres, ns = d->n_spheres, nt = d->n_triangles;
+    for (uint32_t i = 0; i < ns; i++)
+        if (d->spheres[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "sphere %u: material index out of range", i);
+    for (uint32_t i = 0; i < nt; i++)
+        if (d->triangles[i].material >= d->n_materials) return rt_fail(RT_ERR_INVALID_ARGUMENT, "triangle %u: material index out of range", i);
+
+    const bool verbose = getenv("RT_BVH_VERBOSE") != nullptr;  // stage timings on stderr (tuning)
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char *name) {
+        if (!verbose) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rt_bvh] %-28s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+    out = FlatScene();
+    std::vector<uint8_t> transmissive;
+    pack_materials_and_lights(d, out, transmissive);
 
     // ---- BVH references. Every primitive gets one reference. Optionally (RT_BVH_SPLIT_DIV=d > 0)
     // triangles whose longest edge exceeds scene_extent / d are referenced once per cell of a k x k

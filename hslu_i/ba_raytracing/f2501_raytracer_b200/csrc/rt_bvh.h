@@ -63,6 +63,10 @@ struct FlatScene {
     uint32_t max_depth = 0;
 };
 
+// pointer / count checks of a scene description; materials and lights in device layout (shared with the device builder)
+int check_scene_desc(const rt_scene_desc *desc);
+void pack_materials_and_lights(const rt_scene_desc *desc, FlatScene &out, std::vector<uint8_t> &transmissive);
+
 // Validates `desc` (indices, pointers) and builds the flattened scene. Returns RT_OK or an error
 // (message via rt_set_error).
 int build_flat_scene(const rt_scene_desc *desc, FlatScene &out);

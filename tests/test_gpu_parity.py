@@ -237,6 +237,68 @@ def test_large_synthetic_mesh(pkg, oracle_mod):
         dev.close()
 
 
+@pytest.mark.parametrize("which", ["semesterbild", "relief"])
+def test_device_bvh_builder(pkg, oracle_mod, monkeypatch, which):
+    """rt_bvh_device.cu (Morton codes, radix sort, Karras tree, level-wise BVH4 collapse on the GPU) against the host's
+    binned-SAH builder: raw queries give the primitive and distance of the linear scan bit for bit, shadow queries the
+    same occlusion, the rendered frame passes the parity bar, and the builder reports itself in rt_scene_get_info."""
+    from hslu_i.ba_raytracing.f2501_raytracer_b200.synthetic import large_mesh_scene
+
+    if which == "semesterbild":   # 14.6 k primitives: forced (the default for small scenes is the host builder)
+        feat, kw = "high_quality,simd_render", dict(width=384, height=320, n_light_clouds=512)
+        flat = pkg.example_scene("semesterbild", feat).flatten()
+        mode, n_rays = oracle_mod.BRUTE, 12000
+    else:                         # 524 k triangles: the device builder is the default from 2^17 primitives on
+        feat, kw = "high_quality,realistic,simd_render", dict(width=270, height=225, n_light_clouds=256)
+        flat = large_mesh_scene(feat, nx=512, ny=512).flatten()
+        mode, n_rays = oracle_mod.BVH, 50000
+    monkeypatch.setenv("RT_BVH_BUILDER", "host")
+    host = pkg.DeviceScene(flat)
+    monkeypatch.setenv("RT_BVH_BUILDER", "device")
+    dev = pkg.DeviceScene(flat)
+    monkeypatch.delenv("RT_BVH_BUILDER")
+    auto = pkg.DeviceScene(flat)
+    try:
+        hi, di = host.bvh_info(), dev.bvh_info()
+        assert hi["builder"] == 0 and di["builder"] == 1 and auto.bvh_info()["builder"] == (1 if which == "relief" else 0)
+        assert di["n_slots"] == flat.n_primitives and 0 < di["bvh_depth"] <= 20 and di["n_nodes"] < flat.n_primitives
+        rng = np.random.default_rng(17)
+        rays = random_rays(rng, n_rays)
+        t_o, p_o = oracle_mod.trace_closest(flat.desc(), rays, 0, mode)
+        for scene in (dev, host):
+            t_g, p_g = scene.trace_closest(rays)
+            assert np.array_equal(p_g, p_o) and np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))
+        md = rng.uniform(0.05, 2.5, n_rays).astype(np.float32)
+        s_d, s_h = dev.trace_shadow(rays, md), host.trace_shadow(rays, md)
+        assert np.array_equal(s_d[:, 0], s_h[:, 0]) and np.allclose(s_d[:, 1:], s_h[:, 1:], rtol=0, atol=2e-6)
+        ray_nan = np.array([[0, 0, 0, float("nan"), 0, 1]], np.float32)   # the NaN-ray corner needs the lowest-index triangle's slot
+        assert np.array_equal(dev.trace_closest(ray_nan)[1], host.trace_closest(ray_nan)[1])
+        rc = pkg.RenderConfig.from_features(feat, 3, **kw)
+        a, _ = dev.render(rc)
+        b, _ = host.render(rc)
+        assert np.array_equal(a.hit_mask, b.hit_mask) and (chan_diff(a.buffer, b.buffer) <= 1).mean() >= 0.9999
+        W, H = rc.cfg.width, rc.cfg.height
+        ys, xs = np.mgrid[0:H:3, 0:W:3]
+        pix = (ys * W + xs).astype(np.uint32).ravel()
+        o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+        assert_image_parity(a, o_argb, o_mask, pix)
+        # the same build twice gives the same tree (prefix sums, no atomics in the numbering)
+        again = pkg.DeviceScene(flat) if which == "relief" else None
+        if again is not None:
+            assert again.bvh_info()["n_nodes"] == auto.bvh_info()["n_nodes"]
+            again.close()
+    finally:
+        host.close()
+        dev.close()
+        auto.close()
+    bad = pkg.example_scene("test_scene", "").flatten()
+    bad.triangles["v2"][3, 1] = np.nan
+    monkeypatch.setenv("RT_BVH_BUILDER", "device")
+    with pytest.raises(pkg.RtError) as e:
+        pkg.DeviceScene(bad)
+    assert e.value.code == pkg._lib.RT_ERR_INVALID_ARGUMENT
+
+
 def test_c5_at_the_benchmarked_size(pkg, oracle_mod):
     """BASELINE configs[4] at the size bench.py measures: 4 194 304-triangle relief + semesterbild objects,
     `extreme_quality,realistic,high_resolution,simd_render` = 1620x1350, 24 samples, 140 shadow rays, depth 21/21.
@@ -251,7 +313,8 @@ def test_c5_at_the_benchmarked_size(pkg, oracle_mod):
     assert len(flat.triangles) == 2 * 2048 * 1024 + 48
     dev = pkg.DeviceScene(flat)
     try:
-        assert dev.bvh_info()["n_slots"] >= flat.n_primitives
+        info = dev.bvh_info()
+        assert info["n_slots"] >= flat.n_primitives and info["builder"] == 1  # built on the GPU (rt_bvh_device.cu)
         rng = np.random.default_rng(40)
         rays = random_rays(rng, 100000)
         # half of the rays aimed at the relief from the camera side, so that most of them end in the fine mesh
@@ -260,7 +323,7 @@ def test_c5_at_the_benchmarked_size(pkg, oracle_mod):
         t_g, p_g = dev.trace_closest(rays)
         t_o, p_o = oracle_mod.trace_closest(flat.desc(), rays, 0, oracle_mod.BVH)
         assert np.array_equal(p_g, p_o) and np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))
-        assert (p_o >= 9 + 48).mean() > 0.3  # the relief itself is hit
+        assert (p_o >= 9 + 48).mean() > 0.1  # the relief itself is hit
         md = rng.uniform(0.05, 2.5, len(rays)).astype(np.float32)
         s_g = dev.trace_shadow(rays, md)
         s_o = oracle_mod.trace_shadow(flat.desc(), rays, md, 0, oracle_mod.BVH)
