@@ -43,8 +43,11 @@ struct rt_scene {
     size_t samples_cap = 0;
     uint4 *primary_hits = nullptr;
     size_t primary_cap = 0;
-    DirectState *direct_state = nullptr;  // running light sums between the passes of direct_kernel
+    DirectState *direct_state = nullptr;  // running light sums between the light groups of direct_kernel (bounded: windows)
     size_t direct_cap = 0;
+    unsigned int *chain_done = nullptr;   // per batch of a window: tag of the window's last unit (slot reuse across windows)
+    size_t chain_done_cap = 0;
+    size_t info_scratch_bytes = 0;        // chained-record scratch of the last direct-lighting frame
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
     HeavyQueue *heavy_queue = nullptr;      // list of deferred (very expensive) units of direct_kernel
     RenderParams *d_params = nullptr;       // global-memory copy of the kernel parameters for direct_kernel's out-of-line paths
@@ -364,23 +367,10 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         if ((uint64_t)warps_needed * passes >= (1ull << 32))
             return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu work units (limit 2^32); render it in row tiles",
                            (unsigned long long)warps_needed * passes);
-        {
-            const size_t before = s->direct_cap;
-            // one chained record per (light group, sample); the last group writes the sample itself
-            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)warps_needed * 32 * (passes > 1 ? passes - 1 : 1), 1) * sizeof(DirectState));
-            if (rc) return rc;
-            if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
-        }
         RenderParams pd = p;
         if (n_groups == 0) {  // no lights: ambient term only
             pd.LM = 0;
             pd.M = 1;
-        }
-        // tags of this frame's chained records: never equal to a tag left in the buffer by an earlier frame
-        s->frame_serial += MAX_PASSES;
-        if (s->frame_serial > 0x7FFF0000u) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
-            CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
-            s->frame_serial = MAX_PASSES;
         }
         // shadow beams need M copies per light and usable bounds of the cloud points
         const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
@@ -392,6 +382,34 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         uint32_t defer_below = 100;
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
+        // Chained records between the light groups of a batch (direct_kernel): windows of `chain_window` batches with
+        // two generations each; the DEFER variant keeps one window with every generation.
+        uint32_t chain_window = 16384;
+        if (const char *e = getenv("RT_CHAIN_WINDOW")) chain_window = (uint32_t)std::max(1, atoi(e));  // tests: tiny windows
+        chain_window = defer ? warps_needed : std::min(chain_window, warps_needed);
+        const uint32_t n_windows = (warps_needed + chain_window - 1) / chain_window;
+        const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;
+        {
+            const size_t before = s->direct_cap, before_done = s->chain_done_cap;
+            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)chain_window * 32 * gens, 1) * sizeof(DirectState));
+            if (rc) return rc;
+            if ((rc = grow(s->chain_done, s->chain_done_cap, (size_t)chain_window * sizeof(unsigned int)))) return rc;
+            if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
+            if (s->chain_done_cap != before_done) CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
+        }
+        // tags of this frame's chained records, one per (window, group): never equal to a tag an earlier frame left behind
+        const uint64_t tags = (uint64_t)n_windows * passes + 1;
+        if (tags >= 0x7FFF0000ull) return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call (%llu chain tags)", (unsigned long long)tags);
+        if (s->frame_serial == 0 || (uint64_t)s->frame_serial + tags > 0x7FFF0000ull) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
+            CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
+            CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
+            s->frame_serial = 1;
+        }
+        const uint32_t frame_tag = s->frame_serial;
+        s->frame_serial += (uint32_t)tags;
+        pd.chain_window = chain_window;
+        pd.chain_done = s->chain_done;
+        s->info_scratch_bytes = s->direct_cap + s->chain_done_cap;
         using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *,
                                   unsigned int *);
         kernel_t kernel;
@@ -426,7 +444,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         snprintf(s->last_kernel, sizeof(s->last_kernel), "direct_kernel<%s,%s,%s>", count ? "true" : "false", beams ? "true" : "false",
                  defer ? "true" : "false");
         s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, s->frame_serial, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
                                                   s->d_watchdog);
         CU_CHECK(cudaGetLastError());
         if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
@@ -746,7 +764,7 @@ extern "C" {
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->d_watchdog};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->d_watchdog, s->chain_done};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->h_params) cudaFreeHost(s->h_params);

@@ -61,6 +61,8 @@ struct RenderParams {
     uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
     uint32_t heavy_cap;    // direct_kernel: deferred units per launch (<= HEAVY_CAP; beyond: processed in place)
     uint32_t defer_all;    // tests only (RT_DEFER_ALL): every unit asks for deferral
+    uint32_t chain_window; // direct_kernel: batches per window of the chained records (see direct_kernel)
+    unsigned int *chain_done;  // per batch of a window: tag of the window's last unit of that batch (slot reuse)
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
     uint4 *primary_hits;           // n_items: closest hit of every primary sample (primary_kernel): bits t, slot, prim, meta
     unsigned int *work_counter;
@@ -597,6 +599,17 @@ __global__ void __launch_bounds__(128) primary_kernel(const RenderParams p) {
 // 16-byte store, so no fence -- and no L1 invalidation -- is needed); the predecessor was handed
 // out a whole group earlier, so the consumer practically never waits.  19 shadow batches per unit
 // instead of 95 and a single tail per frame is what keeps 8-GPU strong scaling efficient.
+//
+// Record storage is BOUNDED: the batches are processed in windows of `chain_window` batches (all light groups of
+// a window before the next window starts), and a window keeps two generations of records, indexed by the parity
+// of the light group -- the writer of (group g, batch b) has waited for group g-1, which read group g-2 before it
+// wrote, so the slot of g-2 is free.  Across windows the slot's last reader is found through the chain as well:
+// the LAST group's unit of (window w, batch b) publishes a tag in chain_done[b] (st.release), and the FIRST
+// group's unit of (window w+1, batch b) waits for it (ld.acquire) before it overwrites the slot; in practice it
+// never waits (that unit finished a whole window ago).  32 MB of records for any frame size instead of
+// S*W*H*(L-1)*32 B (1 GB for the headline frame), and the records are consumed while still in L2.
+// (The DEFER variant -- small launches only -- keeps one window and every generation: its deferred units are
+// finished at the end of the launch and need their predecessors' records until then.)
 struct DirectState {  // running light sums of one sample: (sum.rgb, bits tag) twice
     float4 d, s;
 };
@@ -609,6 +622,15 @@ RT_DEV float4 ld_relaxed_gpu(const float4 *ptr) {
 }
 RT_DEV void st_relaxed_gpu(float4 *ptr, float4 v) {
     asm volatile("st.relaxed.gpu.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+RT_DEV unsigned int ld_acquire_gpu_u32(const unsigned int *ptr) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+    return v;
+}
+RT_DEV void st_release_gpu_u32(unsigned int *ptr, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
 #ifdef RT_DBG_TAIL  // tuning experiments only: per-warp timeline of direct_kernel (rt_dbg_tail in rt_api.cu)
@@ -846,7 +868,9 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const bool packet_noaa = (p.flags & RT_FLAG_PACKET_SEMANTICS) && !(p.flags & RT_FLAG_ANTI_ALIASING);
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
-    const size_t chain_stride = (size_t)n_batches * 32u;  // one record per (group, sample): a record is never overwritten by a later group
+    const uint32_t window = DEFER ? n_batches : p.chain_window;  // batches per window (>= 1)
+    const uint32_t window_units = window * n_groups;
+    const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
     Counters cn = {0, 0, 0, 0, 0, 0};
 #ifdef RT_DBG_TAIL
@@ -865,12 +889,32 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         dbg_last_start = dbg_globaltimer();
         dbg_cur_info = (unsigned long long)unit << 32;
 #endif
-        const uint32_t group_index = unit / n_batches, batch = unit - group_index * n_batches;
+        // unit -> (window, light group, batch): all groups of a window's batches before the next window
+        const uint32_t win = unit / window_units, in_win = unit - win * window_units;
+        const uint32_t win_batches = min(window, n_batches - win * window);  // (the last window may be short)
+        const uint32_t group_index = in_win / win_batches, b_in_win = in_win - group_index * win_batches;
+        const uint32_t batch = win * window + b_in_win;
         const bool last = group_index + 1 == n_groups;
         const uint32_t item = batch * 32u + lane;
         const SampleRec r = rebuild_sample(p, item);
-        DirectState *const own_rec = state + (size_t)group_index * chain_stride + item;
-        const DirectState *const prev_rec = own_rec - chain_stride;  // (only dereferenced when group_index > 0)
+        // generation of a record: the group itself (DEFER: one window, every generation kept) or its parity
+        const uint32_t gen = DEFER ? group_index : (group_index & 1u), prev_gen = DEFER ? group_index - 1u : (gen ^ 1u);
+        DirectState *const own_rec = state + (size_t)gen * chain_stride + (size_t)b_in_win * 32u + lane;
+        const DirectState *const prev_rec = state + (size_t)prev_gen * chain_stride + (size_t)b_in_win * 32u + lane;  // (only dereferenced when group_index > 0)
+        const uint32_t tag_base = frame_tag + win * n_groups;  // tags are unique per (frame, window, group)
+        if (!DEFER && win > 0 && group_index == 0 && n_groups > 1) {
+            // this unit's records reuse the slots of the previous window: wait until that window's last unit of this
+            // batch -- and with it, through the chain, every reader of those slots -- has finished
+            const unsigned int want_done = tag_base - 1u;  // = tag of (win - 1, last group)
+            if (lane == 0) {
+                for (uint32_t spins = 0; ld_acquire_gpu_u32(p.chain_done + b_in_win) != want_done; spins++)
+                    if (spins > WAIT_SPINS) {
+                        watchdog_trip(watchdog, 6u);
+                        break;
+                    }
+            }
+            __syncwarp();
+        }
         if (COUNT && r.valid && group_index == 0) cn.closest++;
         // lanes of a batch that missed sit the batch out but stay with the warp
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
@@ -887,7 +931,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         if (r.hit) {
             if (group_index > 0) {
                 // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
-                const uint32_t want = frame_tag + group_index - 1u;
+                const uint32_t want = tag_base + group_index - 1u;
                 float4 sd, ss;
 #ifdef RT_DBG_TAIL
                 const unsigned long long dbg_s0 = dbg_globaltimer();
@@ -956,7 +1000,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     idx = __shfl_sync(FULL, idx, 0);
                 }
                 if (idx != 0xFFFFFFFFu) {
-                    defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (frame_tag + group_index) | CHAIN_DEFERRED, !last && r.hit,
+                    defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (tag_base + group_index) | CHAIN_DEFERRED, !last && r.hit,
                                last && r.valid && !r.hit);
 #ifdef RT_DBG_TAIL
                     dbg_helped++;
@@ -1001,7 +1045,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #endif
         if (r.hit) {
             if (!last) {
-                const float tag = __uint_as_float(frame_tag + group_index);
+                const float tag = __uint_as_float(tag_base + group_index);
                 st_relaxed_gpu(&own_rec->d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
                 st_relaxed_gpu(&own_rec->s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
             } else {
@@ -1009,6 +1053,12 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             }
         } else if (r.valid && last) {
             p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        if (!DEFER && last && n_groups > 1 && window < n_batches) {
+            // the window's last unit of this batch: every lane has read its predecessor's record -- the slots of this
+            // batch may be reused by the next window (release: ordered after the loads of all lanes)
+            __syncwarp();
+            if (lane == 0) st_release_gpu_u32(p.chain_done + b_in_win, tag_base + group_index);
         }
     }
     // the queue is empty: work off the deferred units together

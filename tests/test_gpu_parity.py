@@ -517,6 +517,27 @@ def test_deferred_units_are_bit_identical(pkg, scenes, monkeypatch):
         assert np.array_equal(a.buffer, c.buffer) and np.array_equal(a.hit_mask, c.hit_mask)
 
 
+@pytest.mark.parametrize("window", ["3", "64", "1000"])
+def test_chained_records_live_in_a_bounded_window(pkg, scenes, monkeypatch, window):
+    """direct_kernel chains the running light sums of a batch from light group to light group through records in
+    global memory.  The records live in a window of RT_CHAIN_WINDOW batches x 2 generations (default 16384 batches =
+    32 MB for any frame size); a slot is reused by the next window only after the previous window's last unit of that
+    batch has published its tag.  Tiny windows make every unit take that path: same image bit for bit, no watchdog."""
+    feat = "high_quality,simd_render"
+    flat, dev = scenes("semesterbild", feat)
+    rc = pkg.RenderConfig.from_features(feat, 2, width=384, height=320, n_light_clouds=512)
+    monkeypatch.setenv("RT_DEFER_BELOW", "0")      # the variant that windows its records
+    ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    monkeypatch.setenv("RT_CHAIN_WINDOW", window)
+    for _ in range(2):                             # (twice: the second frame finds the first one's tags in the slots)
+        got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+        assert ref.hit_mask.any() and np.array_equal(ref.buffer, got.buffer) and np.array_equal(ref.hit_mask, got.hit_mask)
+    monkeypatch.delenv("RT_CHAIN_WINDOW")
+    monkeypatch.setenv("RT_DEFER_BELOW", "1000000")  # and the deferring variant right after it on the same scratch
+    got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    assert np.array_equal(ref.buffer, got.buffer)
+
+
 @pytest.mark.parametrize("cap", ["16384", "3000", "37", "0"])
 def test_deferral_never_blocks_when_the_list_fills_up(pkg, scenes, monkeypatch, cap):
     """Every unit of the launch asks for deferral (RT_DEFER_ALL, a test hook) -- tens of thousands of units against a
