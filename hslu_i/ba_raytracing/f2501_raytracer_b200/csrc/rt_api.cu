@@ -45,6 +45,18 @@ struct rt_scene {
     size_t primary_cap = 0;
     DirectState *direct_state = nullptr;  // running light sums between the light groups of direct_kernel (bounded: windows)
     size_t direct_cap = 0;
+    // wavefront form of the bounce configs: the path queue of the chunk being rendered
+    PathPoint *wave_points = nullptr;
+    size_t wave_points_cap = 0;
+    float4 *wave_contrib = nullptr;
+    size_t wave_contrib_cap = 0;
+    int32_t *wave_heads = nullptr;
+    size_t wave_heads_cap = 0;
+    unsigned int *wave_count = nullptr, *h_wave_count = nullptr;
+    int paths_ctas_per_sm[2] = {0, 0};
+    bool l2_policy_set = false;
+    cudaStream_t l2_policy_stream = nullptr;
+    uint64_t last_wave_points = 0;
     unsigned int *chain_done = nullptr;   // per batch of a window: tag of the window's last unit (slot reuse across windows)
     size_t chain_done_cap = 0;
     size_t info_scratch_bytes = 0;        // chained-record scratch of the last direct-lighting frame
@@ -67,7 +79,7 @@ struct rt_scene {
     size_t heavy_scratch_cap = 0;
     uint32_t frame_serial = 0;              // base of the chain tags of the current frame
     int ctas_per_sm_direct = 0, ctas_per_sm_direct_count = 0;
-    int direct_ctas_per_sm[6] = {0, 0, 0, 0, 0, 0};  // per direct_kernel variant, filled on first use
+    int direct_ctas_per_sm[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // per direct_kernel variant, filled on first use
     float *clouds_raw = nullptr;  // K x M x 3 cloud points, as handed over
     float4 *clouds = nullptr;     // the same points scaled to scene units (scale_clouds_kernel)
     size_t clouds_raw_cap = 0, clouds_cap = 0;
@@ -263,11 +275,215 @@ static int upload_params(rt_scene *s, const RenderParams &p, cudaStream_t stream
     return RT_OK;
 }
 
+// RT_L2_PERSIST=1 (A/B switch, default off): asks the L2 to keep the BVH node array resident
+// (cudaAccessPolicyWindow on the launching stream).  Only matters for scenes whose nodes + primitives exceed the
+// 126 MB L2 (BASELINE configs[4]); measured in profiles/README.md.
+static void apply_l2_policy(rt_scene *s, cudaStream_t stream) {
+    static const int want = getenv("RT_L2_PERSIST") ? atoi(getenv("RT_L2_PERSIST")) : 0;
+    if (!want || (s->l2_policy_set && s->l2_policy_stream == stream)) return;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
+    const size_t bytes = (size_t)s->n_nodes * 128;
+    const size_t window = std::min<size_t>(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, window);
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    cudaStreamAttrValue attr{};
+    attr.accessPolicyWindow.base_ptr = s->buf_nodes;
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = window ? std::min(1.0f, (float)carve / (float)window) : 0.0f;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    s->l2_policy_set = true;
+    s->l2_policy_stream = stream;
+}
+
+// Direct lighting of `p.n_items` work items -- primary samples (points == false: the frames without bounces) or the
+// shading points of a path queue (points == true: the wavefront form of the bounce configs) -- with direct_kernel.
+static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const RenderParams &p, uint32_t warps_needed, bool count, bool points,
+                                   cudaStream_t stream, uint64_t *launches, bool record_events) {
+    int rc = RT_OK;
+    {
+        // direct lighting only: one pass per light group over all samples
+        const uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);
+        const uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
+        if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
+        if ((uint64_t)warps_needed * passes >= (1ull << 32))
+            return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu work units (limit 2^32); render it in row tiles",
+                           (unsigned long long)warps_needed * passes);
+        RenderParams pd = p;
+        if (n_groups == 0) {  // no lights: ambient term only
+            pd.LM = 0;
+            pd.M = 1;
+        }
+        // shadow beams need M copies per light and usable bounds of the cloud points
+        const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
+                           std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
+        // few units per warp (a rank's share of a multi-GPU frame): the tail of the launch matters more than the
+        // last few per cent of steady-state throughput -> the variant that defers very expensive units
+        const uint32_t resident_warps = (uint32_t)s->sm_count * (uint32_t)std::max(s->ctas_per_sm_direct, 1) * CTA_WARPS;
+        const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / resident_warps);
+        uint32_t defer_below = 100;
+        if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
+        const bool defer = beams && units_per_warp < defer_below;
+        // Chained records between the light groups of a batch (direct_kernel): windows of `chain_window` batches with
+        // two generations each; the DEFER variant keeps one window with every generation.
+        uint32_t chain_window = 16384;
+        if (const char *e = getenv("RT_CHAIN_WINDOW")) chain_window = (uint32_t)std::max(1, atoi(e));  // tests: tiny windows
+        chain_window = defer ? warps_needed : std::min(chain_window, warps_needed);
+        const uint32_t n_windows = (warps_needed + chain_window - 1) / chain_window;
+        const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;
+        {
+            const size_t before = s->direct_cap, before_done = s->chain_done_cap;
+            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)chain_window * 32 * gens, 1) * sizeof(DirectState));
+            if (rc) return rc;
+            if ((rc = grow(s->chain_done, s->chain_done_cap, (size_t)chain_window * sizeof(unsigned int)))) return rc;
+            if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
+            if (s->chain_done_cap != before_done) CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
+        }
+        // tags of this frame's chained records, one per (window, group): never equal to a tag an earlier frame left behind
+        const uint64_t tags = (uint64_t)n_windows * passes + 1;
+        if (tags >= 0x7FFF0000ull) return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call (%llu chain tags)", (unsigned long long)tags);
+        if (s->frame_serial == 0 || (uint64_t)s->frame_serial + tags > 0x7FFF0000ull) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
+            CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
+            CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
+            s->frame_serial = 1;
+        }
+        const uint32_t frame_tag = s->frame_serial;
+        s->frame_serial += (uint32_t)tags;
+        pd.chain_window = chain_window;
+        pd.chain_done = s->chain_done;
+        s->info_scratch_bytes = s->direct_cap + s->chain_done_cap;
+        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *,
+                                  unsigned int *);
+        kernel_t kernel;
+        if (points) {
+            if (count)
+                kernel = beams ? (defer ? direct_kernel<true, true, true, true> : direct_kernel<true, true, false, true>) : direct_kernel<true, false, false, true>;
+            else
+                kernel = beams ? (defer ? direct_kernel<false, true, true, true> : direct_kernel<false, true, false, true>) : direct_kernel<false, false, false, true>;
+        } else if (count)
+            kernel = beams ? (defer ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
+        else
+            kernel = beams ? (defer ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
+        // persistent grid: SMs x resident CTAs of the selected variant (they differ in register budget)
+        const int variant = (points ? 6 : 0) + (count ? 3 : 0) + (beams ? (defer ? 2 : 1) : 0);
+        if (s->direct_ctas_per_sm[variant] == 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
+            s->direct_ctas_per_sm[variant] = n;
+        }
+        int dgrid = s->sm_count * s->direct_ctas_per_sm[variant];
+        dgrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)dgrid, (warps_needed * passes + CTA_WARPS - 1) / CTA_WARPS));
+        HeavyQueue *hq = nullptr;
+        if (defer) {
+            if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
+            pd.heavy_cap = HEAVY_CAP;
+            if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
+            if (const char *e = getenv("RT_DEFER_ALL")) pd.defer_all = atoi(e) != 0;  // tests: every unit asks for deferral
+            rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
+            if (rc) return rc;
+            CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter
+            hq = s->heavy_queue;
+            if ((rc = upload_params(s, pd, stream))) return rc;
+        }
+        unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
+        if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
+        if (record_events)
+            if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
+        snprintf(s->last_kernel, sizeof(s->last_kernel), points ? "paths_kernel + direct_kernel<%s,%s,%s,points> + gather_paths_kernel" : "direct_kernel<%s,%s,%s>",
+                 count ? "true" : "false", beams ? "true" : "false", defer ? "true" : "false");
+        s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
+                                                  s->d_watchdog);
+        CU_CHECK(cudaGetLastError());
+        if (record_events) {
+            if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
+            s->kev_count++;
+        }
+        if (launches) *launches += 1;
+    }
+    return RT_OK;
+}
+
+// Bounce configs, wavefront form (rt_kernels.cuh): per chunk of primary samples, paths_kernel appends the shading
+// points of the reflection / refraction trees to a queue, direct_kernel<.., POINTS> lights the queue, and
+// gather_paths_kernel sums every sample's contributions in path order.  The host reads the number of points after
+// paths_kernel (it sizes the lighting launch), so this path synchronises `stream` once per chunk; a chunk whose
+// points do not fit the queue is rendered again in two halves.
+static int enqueue_wavefront(rt_scene *s, const rt_config *cfg, RenderParams &p, bool count, cudaStream_t stream, uint64_t *launches) {
+    int rc = RT_OK;
+    uint32_t chunk_items = 1u << 22;
+    if (const char *e = getenv("RT_WAVE_CHUNK")) chunk_items = (uint32_t)std::max(32, atoi(e));  // tests: small chunks
+    chunk_items = std::min((chunk_items + 31u) & ~31u, (p.n_items + 31u) & ~31u);
+    uint64_t capacity = std::min<uint64_t>(1ull << 25, std::max<uint64_t>(1ull << 16, 12ull * chunk_items));
+    if (const char *e = getenv("RT_WAVE_POINTS")) capacity = (uint64_t)std::max(64, atoi(e));  // tests: the overflow path
+    if ((rc = grow(s->wave_points, s->wave_points_cap, capacity * sizeof(PathPoint)))) return rc;
+    if ((rc = grow(s->wave_contrib, s->wave_contrib_cap, capacity * sizeof(float4)))) return rc;
+    if ((rc = grow(s->wave_heads, s->wave_heads_cap, (size_t)chunk_items * sizeof(int32_t)))) return rc;
+    if (!s->wave_count) CU_CHECK(cudaMalloc((void **)&s->wave_count, sizeof(unsigned int)));
+    if (!s->h_wave_count) CU_CHECK(cudaMallocHost((void **)&s->h_wave_count, sizeof(unsigned int)));
+    if (s->paths_ctas_per_sm[count ? 1 : 0] == 0) {
+        int n = 0;
+        cudaError_t e = count ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, paths_kernel<true>, CTA_THREADS, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, paths_kernel<false>, CTA_THREADS, 0);
+        s->paths_ctas_per_sm[count ? 1 : 0] = (e == cudaSuccess && n >= 1) ? n : 1;
+    }
+    p.pq.points = s->wave_points;
+    p.pq.contrib = s->wave_contrib;
+    p.pq.sample_head = s->wave_heads;
+    p.pq.n_points = s->wave_count;
+    p.pq.capacity = (uint32_t)capacity;
+    if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
+    uint64_t total_points = 0;
+    for (uint32_t first = 0; first < p.n_items;) {
+        const uint32_t n = std::min(chunk_items, p.n_items - first);
+        p.pq.first_item = first;
+        p.pq.n_chunk_items = n;
+        CU_CHECK(cudaMemsetAsync(s->wave_count, 0, sizeof(unsigned int), stream));
+        CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
+        int grid = s->sm_count * s->paths_ctas_per_sm[count ? 1 : 0];
+        grid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)grid, ((n + 31) / 32 + CTA_WARPS - 1) / CTA_WARPS));
+        p.tail_div = 2u * (uint32_t)grid * CTA_WARPS;
+        if (count)
+            paths_kernel<true><<<grid, CTA_THREADS, 0, stream>>>(p);
+        else
+            paths_kernel<false><<<grid, CTA_THREADS, 0, stream>>>(p);
+        CU_CHECK(cudaGetLastError());
+        if (launches) *launches += 1;
+        CU_CHECK(cudaMemcpyAsync(s->h_wave_count, s->wave_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+        CU_CHECK(cudaStreamSynchronize(stream));
+        const unsigned int n_points = *s->h_wave_count;
+        if (n_points > capacity) {  // the queue is too small for this chunk: two halves
+            if (n <= 32) return rt_fail(RT_ERR_OUT_OF_MEMORY, "wavefront: %u shading points of 32 samples do not fit the path queue (%llu)", n_points,
+                                        (unsigned long long)capacity);
+            chunk_items = std::max(32u, ((n / 2) + 31u) & ~31u);
+            continue;
+        }
+        if (n_points) {
+            RenderParams pl = p;
+            pl.n_items = n_points;
+            if ((rc = enqueue_direct_lighting(s, cfg, pl, (n_points + 31u) / 32u, count, true, stream, launches, false))) return rc;
+        }
+        gather_paths_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p);
+        CU_CHECK(cudaGetLastError());
+        if (launches) *launches += 1;
+        total_points += n_points;
+        first += n;
+    }
+    if (total_points == 0) snprintf(s->last_kernel, sizeof(s->last_kernel), "paths_kernel + gather_paths_kernel");
+    if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
+    s->kev_count++;
+    s->last_wave_points = total_points;
+    return RT_OK;
+}
+
 // enqueue render + resolve on `stream`; slab outputs are device pointers
 static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, uint32_t *d_argb, uint8_t *d_mask, cudaStream_t stream,
                           uint64_t *launches, bool to_frame = false) {
     fill_params(s, cfg, p);
     s->frame_has_watchdog = false;
+    apply_l2_policy(s, stream);
     // the scene's scratch buffers and cached tables are shared by all calls: a call on another stream than the
     // previous one is ordered after it
     if (s->has_last && s->last_stream != stream) CU_CHECK(cudaStreamWaitEvent(stream, s->ev_last, 0));
@@ -339,7 +555,11 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
             p.cloud_hi[k] = s->cloud_hi[k];
         }
     }
-    if (bounces) {
+    bool wavefront = bounces;
+    if (const char *e = getenv("RT_WAVEFRONT")) wavefront = wavefront && atoi(e) != 0;  // 0: the round-1 megakernel (A/B runs, tests)
+    if (wavefront) {
+        if ((rc = enqueue_wavefront(s, cfg, p, count, stream, launches))) return rc;
+    } else if (bounces) {
         // per-sample reflection / refraction trees: persistent megakernel
         CU_CHECK(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
         // shadow beams (lanes lighting their own hit) need M copies per light and usable bounds of the cloud points
@@ -360,96 +580,7 @@ static int enqueue_render(rt_scene *s, const rt_config *cfg, RenderParams &p, ui
         s->kev_count++;
         if (launches) *launches += 1;
     } else {
-        // direct lighting only: one pass per light group over all samples
-        const uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);
-        const uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
-        if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
-        if ((uint64_t)warps_needed * passes >= (1ull << 32))
-            return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu work units (limit 2^32); render it in row tiles",
-                           (unsigned long long)warps_needed * passes);
-        RenderParams pd = p;
-        if (n_groups == 0) {  // no lights: ambient term only
-            pd.LM = 0;
-            pd.M = 1;
-        }
-        // shadow beams need M copies per light and usable bounds of the cloud points
-        const bool beams = pd.M > 1 && !(cfg->flags & RT_FLAG_PER_RAY_SHADOWS) && std::isfinite(pd.cloud_lo[0] + pd.cloud_lo[1] + pd.cloud_lo[2]) &&
-                           std::isfinite(pd.cloud_hi[0] + pd.cloud_hi[1] + pd.cloud_hi[2]);
-        // few units per warp (a rank's share of a multi-GPU frame): the tail of the launch matters more than the
-        // last few per cent of steady-state throughput -> the variant that defers very expensive units
-        const uint32_t resident_warps = (uint32_t)s->sm_count * (uint32_t)std::max(s->ctas_per_sm_direct, 1) * CTA_WARPS;
-        const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / resident_warps);
-        uint32_t defer_below = 100;
-        if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
-        const bool defer = beams && units_per_warp < defer_below;
-        // Chained records between the light groups of a batch (direct_kernel): windows of `chain_window` batches with
-        // two generations each; the DEFER variant keeps one window with every generation.
-        uint32_t chain_window = 16384;
-        if (const char *e = getenv("RT_CHAIN_WINDOW")) chain_window = (uint32_t)std::max(1, atoi(e));  // tests: tiny windows
-        chain_window = defer ? warps_needed : std::min(chain_window, warps_needed);
-        const uint32_t n_windows = (warps_needed + chain_window - 1) / chain_window;
-        const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;
-        {
-            const size_t before = s->direct_cap, before_done = s->chain_done_cap;
-            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)chain_window * 32 * gens, 1) * sizeof(DirectState));
-            if (rc) return rc;
-            if ((rc = grow(s->chain_done, s->chain_done_cap, (size_t)chain_window * sizeof(unsigned int)))) return rc;
-            if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags
-            if (s->chain_done_cap != before_done) CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
-        }
-        // tags of this frame's chained records, one per (window, group): never equal to a tag an earlier frame left behind
-        const uint64_t tags = (uint64_t)n_windows * passes + 1;
-        if (tags >= 0x7FFF0000ull) return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call (%llu chain tags)", (unsigned long long)tags);
-        if (s->frame_serial == 0 || (uint64_t)s->frame_serial + tags > 0x7FFF0000ull) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
-            CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
-            CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
-            s->frame_serial = 1;
-        }
-        const uint32_t frame_tag = s->frame_serial;
-        s->frame_serial += (uint32_t)tags;
-        pd.chain_window = chain_window;
-        pd.chain_done = s->chain_done;
-        s->info_scratch_bytes = s->direct_cap + s->chain_done_cap;
-        using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *,
-                                  unsigned int *);
-        kernel_t kernel;
-        if (count)
-            kernel = beams ? (defer ? direct_kernel<true, true, true> : direct_kernel<true, true, false>) : direct_kernel<true, false, false>;
-        else
-            kernel = beams ? (defer ? direct_kernel<false, true, true> : direct_kernel<false, true, false>) : direct_kernel<false, false, false>;
-        // persistent grid: SMs x resident CTAs of the selected variant (they differ in register budget)
-        const int variant = (count ? 3 : 0) + (beams ? (defer ? 2 : 1) : 0);
-        if (s->direct_ctas_per_sm[variant] == 0) {
-            int n = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, CTA_THREADS, 0) != cudaSuccess || n < 1) n = 1;
-            s->direct_ctas_per_sm[variant] = n;
-        }
-        int dgrid = s->sm_count * s->direct_ctas_per_sm[variant];
-        dgrid = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)dgrid, (warps_needed * passes + CTA_WARPS - 1) / CTA_WARPS));
-        HeavyQueue *hq = nullptr;
-        if (defer) {
-            if (!s->heavy_queue) CU_CHECK(cudaMalloc((void **)&s->heavy_queue, sizeof(HeavyQueue)));
-            pd.heavy_cap = HEAVY_CAP;
-            if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
-            if (const char *e = getenv("RT_DEFER_ALL")) pd.defer_all = atoi(e) != 0;  // tests: every unit asks for deferral
-            rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
-            if (rc) return rc;
-            CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter
-            hq = s->heavy_queue;
-            if ((rc = upload_params(s, pd, stream))) return rc;
-        }
-        unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
-        if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
-        if (cudaEvent_t e = kernel_event(s, 0)) cudaEventRecord(e, stream);
-        snprintf(s->last_kernel, sizeof(s->last_kernel), "direct_kernel<%s,%s,%s>", count ? "true" : "false", beams ? "true" : "false",
-                 defer ? "true" : "false");
-        s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
-                                                  s->d_watchdog);
-        CU_CHECK(cudaGetLastError());
-        if (cudaEvent_t e = kernel_event(s, 1)) cudaEventRecord(e, stream);
-        s->kev_count++;
-        if (launches) *launches += 1;
+        if ((rc = enqueue_direct_lighting(s, cfg, p, warps_needed, count, false, stream, launches, true))) return rc;
     }
     uint32_t n_pix = p.local_rows * p.width;
     resolve_kernel<<<(n_pix + 255) / 256, 256, 0, stream>>>(p, d_argb, d_mask, to_frame ? 1 : 0);
@@ -674,6 +805,7 @@ static int scene_from_device_build(const rt_scene_desc *desc, int device, rt_sce
     s->d.mats = (const float4 *)s->buf_mats;
     s->d.lights = (const float4 *)s->buf_lights;
     s->d.n_prims = bvh.n_slots;
+    s->d.n_nodes = bvh.n_nodes;
     s->d.n_lights = desc->n_lights;
     s->d.nan_hit_slot = bvh.nan_hit_slot;
     s->d.nan_hit_slot_culled = bvh.nan_hit_slot_culled;
@@ -718,6 +850,7 @@ static int scene_from_flat(const rtb::FlatScene &flat, int device, double build_
     s->d.mats = (const float4 *)s->buf_mats;
     s->d.lights = (const float4 *)s->buf_lights;
     s->d.n_prims = flat.n_prims;
+    s->d.n_nodes = flat.n_nodes;
     s->d.n_lights = flat.n_lights;
     s->d.nan_hit_slot = flat.nan_hit_slot;
     s->d.nan_hit_slot_culled = flat.nan_hit_slot_culled;
@@ -764,11 +897,12 @@ extern "C" {
 void rt_scene_destroy(rt_scene *s) {
     if (!s) return;
     cudaSetDevice(s->device);
-    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->d_watchdog, s->chain_done};
+    void *bufs[] = {s->buf_nodes, s->buf_prims, s->buf_shade, s->buf_mats, s->buf_lights, s->samples, s->primary_hits, s->direct_state, s->pass_counters, s->heavy_queue, s->heavy_scratch, s->d_params, s->clouds, s->clouds_raw, s->work_counter, s->counters, s->slab_argb, s->d_watchdog, s->chain_done, s->wave_points, s->wave_contrib, s->wave_heads, s->wave_count};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (s->h_params) cudaFreeHost(s->h_params);
     if (s->h_watchdog) cudaFreeHost(s->h_watchdog);
+    if (s->h_wave_count) cudaFreeHost(s->h_wave_count);
     if (s->pinned_argb) cudaFreeHost(s->pinned_argb);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->ev0) cudaEventDestroy(s->ev0);

@@ -40,6 +40,23 @@ constexpr int MAX_AA = 24;
 constexpr int MAX_SM_LIGHTS = 8; // cloud indices cached in shared memory for up to 8 lights
 constexpr int TILE_W = 8, TILE_H = 4;  // work-item order: 8x4-pixel tiles, samples innermost
 
+// Wavefront form of the bounce configs (paths_kernel -> direct_kernel<.., POINTS> -> gather_paths_kernel): one
+// shading point of a sample's reflection / refraction tree, 64 B.
+struct PathPoint {
+    float4 a;  // P.xyz, t (distance of the hit along its ray: attenuation)
+    float4 b;  // N.xyz, bits(material index)
+    float4 c;  // d.xyz (normalised direction of the ray that hit), bits(pixel x | pixel y << 16)
+    float4 w;  // weight.rgb of the point's local colour in its sample, bits(link: previous point of the sample / next after gather's reversal)
+};
+struct PathQueue {
+    PathPoint *points;
+    float4 *contrib;           // per point: weight * local colour (direct_kernel<.., POINTS>)
+    int32_t *sample_head;      // per sample of the chunk: its LAST point (-1: the primary ray missed)
+    unsigned int *n_points;    // points appended so far (may exceed capacity: overflow)
+    uint32_t capacity;
+    uint32_t first_item, n_chunk_items;  // the chunk of primary samples (work items) being traced
+};
+
 struct RenderParams {
     DScene sc;
     uint32_t width, height, flags;
@@ -63,6 +80,7 @@ struct RenderParams {
     uint32_t defer_all;    // tests only (RT_DEFER_ALL): every unit asks for deferral
     uint32_t chain_window; // direct_kernel: batches per window of the chained records (see direct_kernel)
     unsigned int *chain_done;  // per batch of a window: tag of the window's last unit of that batch (slot reuse)
+    PathQueue pq;          // bounce configs: the shading points of the chunk being rendered
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
     uint4 *primary_hits;           // n_items: closest hit of every primary sample (primary_kernel): bits t, slot, prim, meta
     unsigned int *work_counter;
@@ -280,6 +298,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel(const RenderParams p, const RenderParams *gp) {
     __shared__ WarpShared smem[CTA_WARPS];
     WarpShared &ws = smem[threadIdx.x >> 5];
+    stage_top_nodes(p.sc);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const DScene &sc = p.sc;
@@ -565,11 +584,246 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
     }
 }
 
+// ---- wavefront form of the bounce configs -------------------------------------------------------------------
+// render_kernel above lights every shading point where it finds it, inside the divergent path walk: thin bounce
+// tails leave most lanes of a warp idle exactly where 95-140 shadow rays per point are due.  The wavefront form
+// separates the two: paths_kernel walks the reflection / refraction trees (closest-hit rays only -- which children a
+// hit spawns and with which weights depends on geometry and material alone, not on the lighting) and appends every
+// shading point to a queue; direct_kernel<.., POINTS> then lights the queue like it lights primary hits -- full
+// warps of 32 points, one shadow beam per (point, light), chained light groups, deferral of very expensive units;
+// gather_paths_kernel adds a sample's contributions in the order the path walk met them (the same float sums as
+// render_kernel's `acc + w * local`, so the frame is bit-identical).  The frame is processed in chunks of primary
+// samples so that the queue stays bounded.
+template <bool COUNT>
+__global__ void __launch_bounds__(CTA_THREADS, 4) paths_kernel(const RenderParams p) {
+    stage_top_nodes(p.sc);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const DScene &sc = p.sc;
+    const PathQueue &pq = p.pq;
+    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
+    const bool refl_on = (p.flags & RT_FLAG_REFLECTIONS) != 0;
+    const bool refr_on = (p.flags & RT_FLAG_REFRACTIONS) != 0;
+    Counters cn = {0, 0, 0, 0, 0, 0};
+
+    PathRec stack[PATH_STACK];
+    int sp = 0;
+    bool have_item = false, have_ray = false;
+    uint32_t sample_slot = 0, item_index = 0, pix_x = 0, pix_y = 0;
+    int32_t last_point = -1;
+    float3 ro = splat(0.0f), rd = splat(0.0f), rw = splat(0.0f);
+    float r_ior = AIR_IOR;
+    int r_depth = -1;  // -1 = None
+    bool r_refl_child = false, r_primary = false;
+
+    for (;;) {
+        // ---------------------------------------------------------------- refill (as render_kernel)
+        if (!have_ray && sp > 0) {
+            PathRec pr = stack[--sp];
+            ro = f3(pr.a.x, pr.a.y, pr.a.z);
+            r_ior = pr.a.w;
+            rd = f3(pr.b.x, pr.b.y, pr.b.z);
+            uint32_t bits = __float_as_uint(pr.b.w);
+            r_depth = (int)(bits & 0xFFFFu);
+            r_refl_child = (bits & PATH_REFL_CHILD) != 0;
+            r_primary = false;
+            rw = f3(pr.c.x, pr.c.y, pr.c.z);
+            have_ray = true;
+        }
+        if (!have_ray && have_item) {  // tree finished: publish the head of the sample's point list
+            pq.sample_head[sample_slot] = last_point;
+            have_item = false;
+        }
+        {
+            const bool need = !have_ray;
+            const uint32_t need_mask = __ballot_sync(FULL, need);
+            if (need_mask) {
+                uint32_t base = 0, grant = 0;
+                const int leader = __ffs(need_mask) - 1;
+                if ((int)lane == leader) {
+                    const uint32_t done = *(volatile unsigned int *)p.work_counter;
+                    const uint32_t left = done < pq.n_chunk_items ? pq.n_chunk_items - done : 0u;
+                    grant = min((uint32_t)__popc(need_mask), max(min(left / p.tail_div + 1u, 32u), 4u));
+                    base = atomicAdd(p.work_counter, grant);
+                }
+                base = __shfl_sync(FULL, base, leader);
+                grant = __shfl_sync(FULL, grant, leader);
+                const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
+                const uint32_t in_chunk = base + rank;
+                const uint32_t item = pq.first_item + in_chunk;
+                const ItemInfo it = decode_item(p, item);
+                if (need && rank < grant && in_chunk < pq.n_chunk_items) {
+                    if (it.valid) {
+                        pix_x = it.x;
+                        pix_y = tile_image_row(p, it.ly);
+                        sample_slot = in_chunk;
+                        item_index = item;
+                        primary_ray(p, pix_x, pix_y, it.s, ro, rd);
+                        rw = splat(1.0f);
+                        r_ior = AIR_IOR;
+                        r_depth = -1;
+                        r_refl_child = false;
+                        r_primary = true;
+                        last_point = -1;
+                        have_item = true;
+                        have_ray = true;
+                    } else {
+                        pq.sample_head[in_chunk] = -1;  // padding item of an edge tile
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, have_ray)) break;
+
+        // ---------------------------------------------------------------- closest hit (per lane)
+        float3 d = splat(0.0f), P = splat(0.0f), N = splat(0.0f);
+        ClosestHit h;
+        h.slot = -1;
+        h.t = 0.0f;
+        h.meta = 0;
+        h.prim = 0;
+        if (have_ray) {
+            d = normalized3(rd);  // Ray::new_with_mask (ray.rs:52-57)
+            if (r_primary) {  // traced by primary_kernel at full width; here only fetched
+                const uint4 ph = p.primary_hits[item_index];
+                h.t = __uint_as_float(ph.x);
+                h.slot = (int32_t)ph.y;
+                h.prim = ph.z;
+                h.meta = ph.w;
+                if (COUNT) cn.closest++;
+            } else {
+                h = trace_closest<COUNT>(sc, ro, d, cull, cn);
+            }
+        }
+        const bool hit = have_ray && h.slot >= 0;
+        // ---------------------------------------------------------------- append the shading point, spawn the children
+        const uint32_t hit_mask = __ballot_sync(FULL, hit);
+        if (hit_mask) {
+            uint32_t base = 0;
+            const int leader = __ffs(hit_mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(pq.n_points, (unsigned int)__popc(hit_mask));
+            base = __shfl_sync(FULL, base, leader);
+            if (hit) {
+                P = ray_at(ro, d, h.t);
+                if (h.meta & rtb::PRIM_SPHERE) {
+                    float4 q0 = __ldg(sc.prims + 4 * (size_t)h.slot);
+                    N = normalized3(P - f3(q0.x, q0.y, q0.z));
+                } else {
+                    float4 sn = __ldg(sc.shade_n + h.slot);
+                    N = f3(sn.x, sn.y, sn.z);
+                }
+                const Material m = load_material(sc, h.meta & rtb::PRIM_MATERIAL_MASK);
+                const float df = attenuation(h.t);
+                // single_raytrace (raytracer_renderer.rs:147-264), linearised: a reflection child's whole subtree is
+                // scaled by attenuation(child.t) (raytracer_renderer.rs:722-727)
+                const float3 w = r_refl_child ? (rw * df) : rw;
+                const uint32_t idx = base + __popc(hit_mask & ((1u << lane) - 1u));
+                if (idx < pq.capacity) {  // (beyond: the host sees n_points > capacity and renders the chunk in two halves)
+                    PathPoint *pt = pq.points + idx;
+                    pt->a = make_float4(P.x, P.y, P.z, h.t);
+                    pt->b = make_float4(N.x, N.y, N.z, __uint_as_float(h.meta & rtb::PRIM_MATERIAL_MASK));
+                    pt->c = make_float4(d.x, d.y, d.z, __uint_as_float(pix_x | (pix_y << 16)));
+                    pt->w = make_float4(w.x, w.y, w.z, __int_as_float(last_point));
+                }
+                last_point = (int32_t)idx;
+                const bool is_transmissive = m.transmissive;
+                const bool is_reflective = (m.metallic > 0.0f) || is_transmissive;
+                const float start_ior = r_ior;
+                if (refl_on && is_reflective) {  // calculate_reflection (raytracer_renderer.rs:526-729)
+                    float ct = dot3(d, N);
+                    bool inside = ct < 0.0f;
+                    float3 inormal = inside ? -N : N;
+                    float new_ior = inside ? m.ior : AIR_IOR;
+                    float eta = inside ? (new_ior / start_ior) : (start_ior / new_ior);
+                    float ci = fabsf(ct);
+                    float sin2 = eta * eta * (1.0f - ci * ci);
+                    bool tir = sin2 >= 1.0f;
+                    bool reflective = (m.metallic > 0.0f) || (is_transmissive && tir);
+                    if (reflective) {
+                        float3 rdir = normalized3(reflected3(d, N));
+                        bool none = (fabsf(rdir.x - 0.0f) <= EPS) && (fabsf(rdir.y - 0.0f) <= EPS) && (fabsf(rdir.z - 0.0f) <= EPS);
+                        int next = r_depth < 0 ? (int)p.refl_depth : max(r_depth - 1, 0);
+                        if (!none && next > 0 && sp < PATH_STACK) {
+                            float3 reflectance, tmp;
+                            compute_fresnel(m, inormal, -d, start_ior, reflectance, tmp);
+                            float3 co = P + rdir * p.eps_d;
+                            float3 cw = w * reflectance;
+                            stack[sp].a = make_float4(co.x, co.y, co.z, start_ior);
+                            stack[sp].b = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float((uint32_t)next | PATH_REFL_CHILD));
+                            stack[sp].c = make_float4(cw.x, cw.y, cw.z, 0.0f);
+                            sp++;
+                        }
+                    }
+                }
+                if (refr_on && is_transmissive) {  // calculate_refractions (raytracer_renderer.rs:279-524)
+                    float ct = dot3(d, N);
+                    bool entering = ct <= 0.0f;
+                    float3 inormal = entering ? -N : N;
+                    float new_ior = entering ? m.ior : AIR_IOR;
+                    float eta = entering ? (new_ior / start_ior) : (start_ior / new_ior);
+                    float inv_eta = 1.0f / eta;
+                    float3 tmp, transmittance;
+                    compute_fresnel(m, inormal, d, inv_eta, tmp, transmittance);
+                    float3 rdir = normalized3(refracted3(d, -inormal, inv_eta));
+                    float op = m.opacity;
+                    int step = (op < 0.5f) ? 2 : 1;
+                    int factor = (op <= 0.3f) ? 3 : ((op < 0.5f) ? 2 : 1);
+                    int next = r_depth < 0 ? (int)p.refr_depth / factor : max(r_depth - step, 0);
+                    if (next > 0 && sp < PATH_STACK) {
+                        float boost = m.boost + 1.0f;
+                        float3 co = P + rdir * p.eps_d;
+                        float3 cw = w * (transmittance * boost);
+                        stack[sp].a = make_float4(co.x, co.y, co.z, new_ior);
+                        stack[sp].b = make_float4(rdir.x, rdir.y, rdir.z, __uint_as_float((uint32_t)next));
+                        stack[sp].c = make_float4(cw.x, cw.y, cw.z, 0.0f);
+                        sp++;
+                    }
+                }
+            }
+        }
+        have_ray = false;
+    }
+    if (COUNT) {
+        atomicAdd(p.counters + 0, cn.closest);
+        atomicAdd(p.counters + 2, cn.box);
+        atomicAdd(p.counters + 3, cn.tri);
+        atomicAdd(p.counters + 4, cn.sph);
+    }
+}
+
+// One thread per primary sample of the chunk: the sample's colour = its points' contributions added in the order
+// the path walk met them (render_kernel's `acc = acc + w * local`).  The list is linked backwards (every point knows
+// its predecessor); it is reversed in place first, then summed front to back.
+__global__ void gather_paths_kernel(const RenderParams p) {
+    const uint32_t in_chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const PathQueue &pq = p.pq;
+    if (in_chunk >= pq.n_chunk_items) return;
+    const ItemInfo it = decode_item(p, pq.first_item + in_chunk);
+    if (!it.valid) return;
+    const uint32_t sample_index = (it.ly * p.width + it.x) * p.S + it.s;
+    int32_t cur = pq.sample_head[in_chunk], next = -1;
+    while (cur >= 0) {  // reverse: afterwards every point links to its successor
+        float *link = &pq.points[cur].w.w;
+        const int32_t prev = __float_as_int(*link);
+        *link = __int_as_float(next);
+        next = cur;
+        cur = prev;
+    }
+    float3 acc = splat(0.0f);
+    const bool valid = next >= 0;  // the first point is the primary hit
+    for (cur = next; cur >= 0; cur = __float_as_int(pq.points[cur].w.w)) {
+        const float4 c = pq.contrib[cur];
+        acc = acc + f3(c.x, c.y, c.z);
+    }
+    p.samples[sample_index] = make_float4(acc.x, acc.y, acc.z, valid ? 1.0f : 0.0f);
+}
+
 // Closest hit of every primary sample, one thread per work item (same item order as render_kernel).
 // Splitting this off keeps the divergent closest-hit traversal at full warp width and lets
 // render_kernel fetch work in small chunks (fine-grained load balance) at no cost.
 template <bool COUNT>
 __global__ void __launch_bounds__(128) primary_kernel(const RenderParams p) {
+    stage_top_nodes(p.sc);
     const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
     const ItemInfo it = decode_item(p, item);
     if (!it.valid) return;
@@ -681,9 +935,35 @@ struct SampleRec {
     float mshininess, t;
     uint32_t sample_index, pix_x, pix_y;
 };
+// POINTS: `item` is a shading point of the path queue instead of a primary sample
+template <bool POINTS>
 RT_DEV SampleRec rebuild_sample(const RenderParams &p, uint32_t item) {
     const DScene &sc = p.sc;
     SampleRec r;
+    if (POINTS) {
+        r.valid = r.hit = item < p.n_items;
+        r.sample_index = item;
+        r.P = r.N = r.d = r.mcolor = splat(0.0f);
+        r.mshininess = r.t = 0.0f;
+        r.transmissive = false;
+        r.pix_x = r.pix_y = 0;
+        if (r.hit) {
+            const PathPoint *pt = p.pq.points + item;
+            const float4 a = __ldg(&pt->a), b = __ldg(&pt->b), c = __ldg(&pt->c);
+            r.P = f3(a.x, a.y, a.z);
+            r.t = a.w;
+            r.N = f3(b.x, b.y, b.z);
+            r.d = f3(c.x, c.y, c.z);
+            const uint32_t pix = __float_as_uint(c.w);
+            r.pix_x = pix & 0xFFFFu;
+            r.pix_y = pix >> 16;
+            const Material m = load_material(sc, __float_as_uint(b.w));
+            r.mcolor = m.color;
+            r.mshininess = m.shininess;
+            r.transmissive = m.transmissive;
+        }
+        return r;
+    }
     const ItemInfo it = decode_item(p, item);
     uint4 ph = make_uint4(0u, 0xFFFFFFFFu, 0u, 0u);
     if (it.valid) ph = p.primary_hits[item];
@@ -719,18 +999,26 @@ RT_DEV SampleRec rebuild_sample(const RenderParams &p, uint32_t item) {
 }
 
 // single_raytrace without bounces (raytracer_renderer.rs:195-257): the last light group publishes the sample
+// POINTS: the point's contribution to its sample, weight * local colour (the `acc + w * local` term of the path walk)
+template <bool POINTS>
 RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float3 sum_d, float3 sum_s) {
     const float3 ambient = (r.mcolor * splat(1.0f)) * 0.08f;
     const float df = attenuation(r.t);
     const float3 direct = (ambient + sum_d) * df;
     const float3 specular = sum_s * df;
     const float3 local = r.transmissive ? specular : (direct + specular);
-    p.samples[r.sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+    if (POINTS) {
+        const float4 w = __ldg(&p.pq.points[r.sample_index].w);
+        const float3 c = f3(w.x, w.y, w.z) * local;
+        p.pq.contrib[r.sample_index] = make_float4(c.x, c.y, c.z, 1.0f);
+    } else {
+        p.samples[r.sample_index] = make_float4(local.x, local.y, local.z, 1.0f);
+    }
 }
 
 // Phase B of direct_kernel (see above).  Out of line, parameters read from their global-memory copy, so
 // that it does not weigh on the register allocation of the unit loop.
-template <bool COUNT>
+template <bool COUNT, bool POINTS>
 __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
                                                 uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog) {
     const RenderParams &p = *gp;
@@ -777,7 +1065,7 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
         unit = __shfl_sync(FULL, unit, 0);
         const uint32_t g = unit / n_batches, b = unit - g * n_batches;
         const uint32_t item = b * 32u + lane;
-        const SampleRec r = rebuild_sample(p, item);
+        const SampleRec r = rebuild_sample<POINTS>(p, item);
         float4 *slab = hscratch + ((size_t)idx * p.M * 32u + lane) * 2u;  // + copy * 64
         if (r.hit) {
             const LightCopy L = load_light(p, g);
@@ -822,7 +1110,7 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                 st_relaxed_gpu(&state[(size_t)g * chain_stride + item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
                 st_relaxed_gpu(&state[(size_t)g * chain_stride + item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
             } else {
-                store_direct_sample(p, r, sum_d, sum_s);
+                store_direct_sample<POINTS>(p, r, sum_d, sum_s);
             }
         }
     }
@@ -857,10 +1145,11 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
 #ifndef RT_DEFER_MIN_CTAS
 #define RT_DEFER_MIN_CTAS 6  // the DEFER variant is better off with 80 registers (measured: -2.3 % on a rank's eighth of C3)
 #endif
-template <bool COUNT, bool BEAM, bool DEFER>
+template <bool COUNT, bool BEAM, bool DEFER, bool POINTS = false>
 __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
                                                                                     unsigned int *counter, DirectState *state, HeavyQueue *hq,
                                                                                     float4 *hscratch, const RenderParams *gp, unsigned int *watchdog) {
+    stage_top_nodes(p.sc);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
     const DScene &sc = p.sc;
@@ -896,7 +1185,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         const uint32_t batch = win * window + b_in_win;
         const bool last = group_index + 1 == n_groups;
         const uint32_t item = batch * 32u + lane;
-        const SampleRec r = rebuild_sample(p, item);
+        const SampleRec r = rebuild_sample<POINTS>(p, item);
         // generation of a record: the group itself (DEFER: one window, every generation kept) or its parity
         const uint32_t gen = DEFER ? group_index : (group_index & 1u), prev_gen = DEFER ? group_index - 1u : (gen ^ 1u);
         DirectState *const own_rec = state + (size_t)gen * chain_stride + (size_t)b_in_win * 32u + lane;
@@ -915,7 +1204,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             }
             __syncwarp();
         }
-        if (COUNT && r.valid && group_index == 0) cn.closest++;
+        if (COUNT && !POINTS && r.valid && group_index == 0) cn.closest++;  // (POINTS: counted where the ray was traced)
         // lanes of a batch that missed sit the batch out but stay with the warp
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
         const uint32_t li0 = p.M > 1 ? group_index : 0u;
@@ -1049,7 +1338,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 st_relaxed_gpu(&own_rec->d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
                 st_relaxed_gpu(&own_rec->s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
             } else {
-                store_direct_sample(p, r, sum_d, sum_s);
+                store_direct_sample<POINTS>(p, r, sum_d, sum_s);
             }
         } else if (r.valid && last) {
             p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1066,7 +1355,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        finish_heavy_units<COUNT>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
+        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif
@@ -1147,6 +1436,7 @@ __global__ void resolve_kernel(const RenderParams p, uint32_t *__restrict__ out_
 
 // debug/parity kernels: raw BVH queries for arbitrary rays
 __global__ void trace_closest_kernel(DScene sc, uint32_t flags, const float *__restrict__ rays, uint32_t n, float *out_t, uint32_t *out_prim) {
+    stage_top_nodes(sc);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Counters cn = {0, 0, 0, 0, 0, 0};
@@ -1159,6 +1449,7 @@ __global__ void trace_closest_kernel(DScene sc, uint32_t flags, const float *__r
 
 __global__ void trace_shadow_kernel(DScene sc, uint32_t flags, const float *__restrict__ rays, const float *__restrict__ max_dist, uint32_t n,
                                     float *out) {
+    stage_top_nodes(sc);
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Counters cn = {0, 0, 0, 0, 0, 0};

@@ -57,6 +57,7 @@ void *emu_scene_create(const rt_scene_desc *desc) {
     s->d.mats = (const float4 *)s->flat.mats.data();
     s->d.lights = (const float4 *)s->flat.lights.data();
     s->d.n_prims = s->flat.n_prims;
+    s->d.n_nodes = s->flat.n_nodes;
     s->d.n_lights = s->flat.n_lights;
     s->d.nan_hit_slot = s->flat.nan_hit_slot;
     s->d.nan_hit_slot_culled = s->flat.nan_hit_slot_culled;

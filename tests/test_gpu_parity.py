@@ -625,6 +625,41 @@ def test_bounce_kernel_beams_equal_per_ray_traversal(pkg, scenes, scene_name, fe
     assert sr["beam_triangle_tests"] == 0 and sb["beam_triangle_tests"] > 0 and sb["box_tests"] < sr["box_tests"]
 
 
+@pytest.mark.parametrize("scene_name,features,kw", [
+    ("main", "default,simd_render", dict(width=285, height=238, n_light_clouds=256)),                    # AA + soft shadows + depth 13/18
+    ("semesterbild", "realistic", dict(width=540, height=450)),                                          # hard shadows, M = 1
+    ("semesterbild", "extreme_quality,realistic,simd_render", dict(width=144, height=120, n_light_clouds=128)),
+    ("test_scene", "simd_render,backface_culling,realistic,soft_shadows", dict(width=380, height=316, n_light_clouds=256)),  # packet no-AA clouds
+])
+def test_wavefront_equals_the_megakernel(pkg, scenes, monkeypatch, scene_name, features, kw):
+    """Bounce configs are rendered as a wavefront (paths_kernel -> direct_kernel<.., POINTS> -> gather_paths_kernel):
+    the path walk only collects shading points, the lighting runs on full warps of points with shadow beams, and the
+    contributions are summed in path order.  Same float sums as the round-1 megakernel (render_kernel, RT_WAVEFRONT=0):
+    bit-identical frame and ray counts -- also when the frame is cut into many chunks and when a chunk's points overflow
+    the queue and the chunk is halved."""
+    L = pkg._lib
+    flat, dev = scenes(scene_name, features)
+    rc = pkg.RenderConfig.from_features(features, 8, **kw)
+    rcc = pkg.RenderConfig.from_features(features, 8, extra_flags=L.FLAG_COUNT_WORK, **kw)
+    monkeypatch.setenv("RT_WAVEFRONT", "0")
+    mega, _ = dev.render(rc)
+    assert dev.dominant_kernel_name().startswith("render_kernel")
+    _, sm = dev.render(rcc)
+    monkeypatch.delenv("RT_WAVEFRONT")
+    wave, _ = dev.render(rc)
+    assert dev.dominant_kernel_name().startswith("paths_kernel")
+    _, sw = dev.render(rcc)
+    assert mega.hit_mask.any() and np.array_equal(wave.buffer, mega.buffer) and np.array_equal(wave.hit_mask, mega.hit_mask)
+    assert (sw["closest_rays"], sw["shadow_rays"]) == (sm["closest_rays"], sm["shadow_rays"])
+    monkeypatch.setenv("RT_WAVE_CHUNK", "4096")       # dozens of chunks
+    chunks, _ = dev.render(rc)
+    assert np.array_equal(chunks.buffer, mega.buffer)
+    monkeypatch.setenv("RT_WAVE_CHUNK", "65536")
+    monkeypatch.setenv("RT_WAVE_POINTS", "30000")     # far too small for a 65536-sample chunk: halved until it fits
+    small, _ = dev.render(rc)
+    assert np.array_equal(small.buffer, mega.buffer) and np.array_equal(small.hit_mask, mega.hit_mask)
+
+
 def test_gpu_frame_vs_reference_render_dense_grid(pkg, scenes):
     """The CUDA path against the reference's OWN committed render (output.png, crate defaults + simd_render):
     1748 pixels on a 25-px grid (tests/golden/output_png_kats.json).  Hit mask identical; colours equal up to
