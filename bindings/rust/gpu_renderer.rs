@@ -41,6 +41,8 @@ pub struct RtConfig {
 }
 #[repr(C)]
 pub struct RtScene { _private: [u8; 0] }
+#[repr(C)]
+pub struct RtMulti { _private: [u8; 0] }
 
 const RT_FLAG_ANTI_ALIASING: u32 = 1 << 0;
 const RT_FLAG_AA_ROTATION_SCALE: u32 = 1 << 1;
@@ -55,6 +57,12 @@ extern "C" {
     fn rt_scene_create(desc: *const RtSceneDesc, device: c_int, out: *mut *mut RtScene) -> c_int;
     fn rt_scene_destroy(scene: *mut RtScene);
     fn rt_render(scene: *mut RtScene, cfg: *const RtConfig, out_argb: *mut u32, out_hit_mask: *mut u8, stats: *mut c_void) -> c_int;
+    // several GPUs, one process: the frame is partitioned inside the call, like ImageBuffer::process_chunks_parallel
+    // (src/image_buffer.rs:48-97) partitions it over the rayon pool
+    fn rt_device_count() -> c_int;
+    fn rt_multi_create(desc: *const RtSceneDesc, devices: *const c_int, n_devices: u32, out: *mut *mut RtMulti) -> c_int;
+    fn rt_multi_destroy(m: *mut RtMulti);
+    fn rt_multi_render(m: *mut RtMulti, cfg: *const RtConfig, out_argb: *mut u32, out_hit_mask: *mut u8, stats: *mut c_void) -> c_int;
     fn rt_sampler_aa_table(seed: u64, samples_per_pixel: u32, randomness: c_int, out: *mut f32, table_len: u32) -> c_int;
     fn rt_sampler_light_clouds(seed: u64, m: u32, n_clouds: u32, out: *mut f32) -> c_int;
 }
@@ -149,9 +157,22 @@ where
 
         // ---- render straight into the ImageBuffer: [AtomicU32; W*H] is layout-identical to [u32; W*H]
         // (#[repr(transparent)], src/image_buffer.rs:9-15); misses are left untouched like the reference.
+        let out = buffer.get_u32_slice().as_ptr() as *mut u32;
+        // RT_GPUS=n (default 1; 0 = every visible GPU): with more than one, rt_multi_* replicates the scene, deals
+        // the image rows out in interleaved tiles and lets every GPU store its rows into the first GPU's frame
+        // over NVLink; the call returns with the whole ImageBuffer filled.
+        let visible = unsafe { rt_device_count() }.max(0) as u32;
+        let gpus: u32 = std::env::var("RT_GPUS").ok().and_then(|s| s.parse().ok()).map(|n: u32| if n == 0 { visible } else { n.min(visible) }).unwrap_or(1);
+        if gpus > 1 {
+            let mut multi: *mut RtMulti = std::ptr::null_mut();
+            check(unsafe { rt_multi_create(&desc, std::ptr::null(), gpus, &mut multi) });
+            let rc = unsafe { rt_multi_render(multi, &cfg, out, std::ptr::null_mut(), std::ptr::null_mut()) };
+            unsafe { rt_multi_destroy(multi) };
+            check(rc);
+            return;
+        }
         let mut dev: *mut RtScene = std::ptr::null_mut();
         check(unsafe { rt_scene_create(&desc, 0, &mut dev) });
-        let out = buffer.get_u32_slice().as_ptr() as *mut u32;
         let rc = unsafe { rt_render(dev, &cfg, out, std::ptr::null_mut(), std::ptr::null_mut()) };
         unsafe { rt_scene_destroy(dev) };
         check(rc);
