@@ -270,7 +270,8 @@ def test_device_bvh_builder(pkg, oracle_mod, monkeypatch, which):
             assert np.array_equal(p_g, p_o) and np.array_equal(t_g.view(np.uint32), t_o.view(np.uint32))
         md = rng.uniform(0.05, 2.5, n_rays).astype(np.float32)
         s_d, s_h = dev.trace_shadow(rays, md), host.trace_shadow(rays, md)
-        assert np.array_equal(s_d[:, 0], s_h[:, 0]) and np.allclose(s_d[:, 1:], s_h[:, 1:], rtol=0, atol=2e-6)
+        free = s_h[:, 0] == 0  # (an occluded query carries no other state: how much it accumulated first depends on the order)
+        assert np.array_equal(s_d[:, 0], s_h[:, 0]) and np.allclose(s_d[free, 1:], s_h[free, 1:], rtol=0, atol=2e-6) and free.any() and not free.all()
         ray_nan = np.array([[0, 0, 0, float("nan"), 0, 1]], np.float32)   # the NaN-ray corner needs the lowest-index triangle's slot
         assert np.array_equal(dev.trace_closest(ray_nan)[1], host.trace_closest(ray_nan)[1])
         rc = pkg.RenderConfig.from_features(feat, 3, **kw)
@@ -729,6 +730,7 @@ def test_progressive_render_overlaps_copy_and_callback_with_the_next_band(pkg, s
         time.sleep(0.0005)
         slept.append(time.perf_counter() - t)
 
+    dev.render_progressive(rc, None, band_rows=64)   # (first use allocates the pinned band buffers and the copy stream)
     prog, st = dev.render_progressive(rc, None, band_rows=64, on_band=on_band)
     assert np.array_equal(prog.buffer, full.buffer) and np.array_equal(prog.hit_mask, full.hit_mask)
     assert len(slept) == 10 and st["overlapped_bands"] >= 7

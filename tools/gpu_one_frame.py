@@ -10,6 +10,10 @@ from hslu_i.ba_raytracing.f2501_raytracer_b200 import DeviceScene  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 flat, rc, features, desc = bench.build_workload(name, 0)
+if len(sys.argv) > 4:  # reduced frame size (ncu captures of the multi-second configs): same scene, fewer pixels
+    from hslu_i.ba_raytracing.f2501_raytracer_b200 import RenderConfig
+
+    rc = RenderConfig.from_features(features, 0, width=int(sys.argv[3]), height=int(sys.argv[4]))
 dev = DeviceScene(flat)
 print(name, desc, dev.bvh_info(), flush=True)
 for i in range(frames):
