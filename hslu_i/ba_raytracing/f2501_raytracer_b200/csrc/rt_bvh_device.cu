@@ -383,26 +383,53 @@ int build_scene_on_device(const rt_scene_desc *d, const std::vector<unsigned cha
         fprintf(stderr, "[rt_bvh_device] %-28s %8.2f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
         t_last = now;
     };
-    Tmp<rt_sphere> d_sph;
-    Tmp<rt_triangle> d_tri;
-    Tmp<unsigned char> d_tm;
-    Tmp<Bounds> d_bounds;
-    Tmp<float4> blo, bhi, nlo, nhi, nodes_tmp;
-    Tmp<unsigned long long> keys_in, keys_out, d_nan;
-    Tmp<uint32_t> vals_in, vals_out, left, right, parent_int, parent_leaf, first, last, level_a, level_b, counts, offsets;
-    Tmp<unsigned int> flags;
-    Tmp<unsigned char> cub_tmp;
+    // every temporary lives in ONE allocation (a cudaMalloc of hundreds of MB costs milliseconds; two dozen of them
+    // were a third of the build time)
+    Tmp<unsigned char> arena;
+    size_t arena_size = 0;
+    auto reserve = [&](size_t bytes) {  // returns the offset of a 256-byte aligned block
+        const size_t at = arena_size;
+        arena_size += (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
+        return at;
+    };
+    rt_sphere *d_sph = nullptr;
+    rt_triangle *d_tri = nullptr;
+    unsigned char *d_tm = nullptr, *cub_tmp = nullptr;
+    Bounds *d_bounds = nullptr;
+    float4 *blo = nullptr, *bhi = nullptr, *nlo = nullptr, *nhi = nullptr, *nodes_tmp = nullptr;
+    unsigned long long *keys_in = nullptr, *keys_out = nullptr, *d_nan = nullptr;
+    uint32_t *vals_in = nullptr, *vals_out = nullptr, *left = nullptr, *right = nullptr, *parent_int = nullptr, *parent_leaf = nullptr, *first = nullptr,
+             *last = nullptr, *level_a = nullptr, *level_b = nullptr, *counts = nullptr, *offsets = nullptr;
+    unsigned int *flags = nullptr;
+    size_t sort_bytes = 0, scan_bytes = 0, tmp_bytes = 0;
     float4 *d_nodes = nullptr, *d_prims = nullptr, *d_shade = nullptr;
     Bounds hb;
     const int grid_n = (int)((n + TPB - 1) / TPB);
     {
-        CUB_OK(d_sph.alloc(ns));
-        CUB_OK(d_tri.alloc(nt));
-        CUB_OK(d_tm.alloc(transmissive.size()));
-        CUB_OK(d_bounds.alloc(1));
-        if (ns) CUB_OK(cudaMemcpy(d_sph.p, d->spheres, (size_t)ns * sizeof(rt_sphere), cudaMemcpyHostToDevice));
-        if (nt) CUB_OK(cudaMemcpy(d_tri.p, d->triangles, (size_t)nt * sizeof(rt_triangle), cudaMemcpyHostToDevice));
-        if (!transmissive.empty()) CUB_OK(cudaMemcpy(d_tm.p, transmissive.data(), transmissive.size(), cudaMemcpyHostToDevice));
+        CUB_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (uint32_t *)nullptr,
+                                               (uint32_t *)nullptr, (int)n, 0, 63));
+        CUB_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (uint32_t *)nullptr, (uint32_t *)nullptr, (int)n));
+        tmp_bytes = std::max(sort_bytes, scan_bytes);
+        const size_t o_sph = reserve((size_t)ns * sizeof(rt_sphere)), o_tri = reserve((size_t)nt * sizeof(rt_triangle)), o_tm = reserve(transmissive.size()),
+                     o_bounds = reserve(sizeof(Bounds)), o_blo = reserve((size_t)n * 16), o_bhi = reserve((size_t)n * 16), o_nlo = reserve((size_t)n * 16),
+                     o_nhi = reserve((size_t)n * 16), o_kin = reserve((size_t)n * 8), o_kout = reserve((size_t)n * 8), o_nan = reserve(16),
+                     o_vin = reserve((size_t)n * 4), o_vout = reserve((size_t)n * 4), o_left = reserve((size_t)n * 4), o_right = reserve((size_t)n * 4),
+                     o_pint = reserve((size_t)n * 4), o_pleaf = reserve((size_t)n * 4), o_first = reserve((size_t)n * 4), o_last = reserve((size_t)n * 4),
+                     o_la = reserve((size_t)n * 4), o_lb = reserve((size_t)n * 4), o_counts = reserve((size_t)n * 4), o_offsets = reserve((size_t)(n + 1) * 4),
+                     o_flags = reserve((size_t)n * 4), o_cub = reserve(tmp_bytes), o_nodes = reserve((size_t)n * 128);  // (fewer than n BVH4 nodes)
+        CUB_OK(arena.alloc(arena_size));
+        unsigned char *base = arena.p;
+        d_sph = (rt_sphere *)(base + o_sph); d_tri = (rt_triangle *)(base + o_tri); d_tm = base + o_tm; d_bounds = (Bounds *)(base + o_bounds);
+        blo = (float4 *)(base + o_blo); bhi = (float4 *)(base + o_bhi); nlo = (float4 *)(base + o_nlo); nhi = (float4 *)(base + o_nhi);
+        keys_in = (unsigned long long *)(base + o_kin); keys_out = (unsigned long long *)(base + o_kout); d_nan = (unsigned long long *)(base + o_nan);
+        vals_in = (uint32_t *)(base + o_vin); vals_out = (uint32_t *)(base + o_vout); left = (uint32_t *)(base + o_left); right = (uint32_t *)(base + o_right);
+        parent_int = (uint32_t *)(base + o_pint); parent_leaf = (uint32_t *)(base + o_pleaf); first = (uint32_t *)(base + o_first); last = (uint32_t *)(base + o_last);
+        level_a = (uint32_t *)(base + o_la); level_b = (uint32_t *)(base + o_lb); counts = (uint32_t *)(base + o_counts); offsets = (uint32_t *)(base + o_offsets);
+        flags = (unsigned int *)(base + o_flags); cub_tmp = base + o_cub; nodes_tmp = (float4 *)(base + o_nodes);
+        stage("scratch arena");
+        if (ns) CUB_OK(cudaMemcpy(d_sph, d->spheres, (size_t)ns * sizeof(rt_sphere), cudaMemcpyHostToDevice));
+        if (nt) CUB_OK(cudaMemcpy(d_tri, d->triangles, (size_t)nt * sizeof(rt_triangle), cudaMemcpyHostToDevice));
+        if (!transmissive.empty()) CUB_OK(cudaMemcpy(d_tm, transmissive.data(), transmissive.size(), cudaMemcpyHostToDevice));
         stage("upload primitives");
         // ---- 1. bounds + validation
         Bounds init;
@@ -412,10 +439,10 @@ int build_scene_on_device(const rt_scene_desc *d, const std::vector<unsigned cha
         }
         init.max_abs = 0;
         init.bad_coord = init.bad_material = 0;
-        CUB_OK(cudaMemcpy(d_bounds.p, &init, sizeof(init), cudaMemcpyHostToDevice));
-        bounds_kernel<<<std::min(grid_n, 148 * 8), TPB>>>(d_sph.p, d_tri.p, ns, n, d->n_materials, d_bounds.p);
+        CUB_OK(cudaMemcpy(d_bounds, &init, sizeof(init), cudaMemcpyHostToDevice));
+        bounds_kernel<<<std::min(grid_n, 148 * 8), TPB>>>(d_sph, d_tri, ns, n, d->n_materials, d_bounds);
         CUB_OK(cudaGetLastError());
-        CUB_OK(cudaMemcpy(&hb, d_bounds.p, sizeof(hb), cudaMemcpyDeviceToHost));
+        CUB_OK(cudaMemcpy(&hb, d_bounds, sizeof(hb), cudaMemcpyDeviceToHost));
         if (hb.bad_coord) {
             rc = rt_fail(RT_ERR_INVALID_ARGUMENT, "a primitive has non-finite coordinates");
             goto done;
@@ -433,73 +460,45 @@ int build_scene_on_device(const rt_scene_desc *d, const std::vector<unsigned cha
         out.box_pad = 1e-4f * max_abs;  // rt_bvh.cpp
         stage("bounds");
         // ---- 2. references
-        CUB_OK(blo.alloc(n));
-        CUB_OK(bhi.alloc(n));
-        CUB_OK(keys_in.alloc(n));
-        CUB_OK(keys_out.alloc(n));
-        CUB_OK(vals_in.alloc(n));
-        CUB_OK(vals_out.alloc(n));
         float3 lo3 = make_float3(slo[0], slo[1], slo[2]);
         float3 inv3 = make_float3(shi[0] > slo[0] ? 1.0f / (shi[0] - slo[0]) : 0.0f, shi[1] > slo[1] ? 1.0f / (shi[1] - slo[1]) : 0.0f,
                                   shi[2] > slo[2] ? 1.0f / (shi[2] - slo[2]) : 0.0f);
-        refs_kernel<<<grid_n, TPB>>>(d_sph.p, d_tri.p, ns, n, out.box_pad, lo3, inv3, blo.p, bhi.p, keys_in.p, vals_in.p);
+        refs_kernel<<<grid_n, TPB>>>(d_sph, d_tri, ns, n, out.box_pad, lo3, inv3, blo, bhi, keys_in, vals_in);
         CUB_OK(cudaGetLastError());
         stage("boxes + Morton codes");
         // ---- 3. sort
-        size_t tmp_bytes = 0;
-        CUB_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, vals_out.p, (int)n, 0, 63));
-        CUB_OK(cub_tmp.alloc(tmp_bytes));
-        CUB_OK(cub::DeviceRadixSort::SortPairs(cub_tmp.p, tmp_bytes, keys_in.p, keys_out.p, vals_in.p, vals_out.p, (int)n, 0, 63));
+        {
+            size_t sb = tmp_bytes;
+            CUB_OK(cub::DeviceRadixSort::SortPairs(cub_tmp, sb, keys_in, keys_out, vals_in, vals_out, (int)n, 0, 63));
+        }
         stage("radix sort");
         // ---- 4. radix tree + boxes
-        CUB_OK(left.alloc(n));
-        CUB_OK(right.alloc(n));
-        CUB_OK(parent_int.alloc(n));
-        CUB_OK(parent_leaf.alloc(n));
-        CUB_OK(first.alloc(n));
-        CUB_OK(last.alloc(n));
-        CUB_OK(nlo.alloc(n));
-        CUB_OK(nhi.alloc(n));
-        CUB_OK(flags.alloc(n));
-        CUB_OK(cudaMemset(flags.p, 0, (size_t)n * sizeof(unsigned int)));
-        radix_tree_kernel<<<grid_n, TPB>>>(keys_out.p, (int)n, left.p, right.p, parent_int.p, parent_leaf.p, first.p, last.p);
+        CUB_OK(cudaMemset(flags, 0, (size_t)n * sizeof(unsigned int)));
+        radix_tree_kernel<<<grid_n, TPB>>>(keys_out, (int)n, left, right, parent_int, parent_leaf, first, last);
         CUB_OK(cudaGetLastError());
-        refit_kernel<<<grid_n, TPB>>>((int)n, vals_out.p, blo.p, bhi.p, left.p, right.p, parent_int.p, parent_leaf.p, nlo.p, nhi.p, flags.p);
+        refit_kernel<<<grid_n, TPB>>>((int)n, vals_out, blo, bhi, left, right, parent_int, parent_leaf, nlo, nhi, flags);
         CUB_OK(cudaGetLastError());
         stage("radix tree + refit");
         // ---- 5. collapse to BVH4, level by level (breadth-first numbering)
-        CUB_OK(level_a.alloc(n));
-        CUB_OK(level_b.alloc(n));
-        CUB_OK(counts.alloc(n));
-        CUB_OK(offsets.alloc(n + 1));
-        CUB_OK(nodes_tmp.alloc(8 * (size_t)n));  // worst case: fewer than n BVH4 nodes
-        size_t scan_bytes = 0;
-        CUB_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts.p, offsets.p, (int)n));
-        if (scan_bytes > tmp_bytes) {
-            cudaFree(cub_tmp.p);
-            cub_tmp.p = nullptr;
-            CUB_OK(cub_tmp.alloc(scan_bytes));
-            tmp_bytes = scan_bytes;
-        }
-        TreeView tv{left.p, right.p, first.p, last.p, vals_out.p, blo.p, bhi.p, nlo.p, nhi.p};
+        TreeView tv{left, right, first, last, vals_out, blo, bhi, nlo, nhi};
         uint32_t root = 0;
-        CUB_OK(cudaMemcpy(level_a.p, &root, sizeof(root), cudaMemcpyHostToDevice));
+        CUB_OK(cudaMemcpy(level_a, &root, sizeof(root), cudaMemcpyHostToDevice));
         uint32_t n_level = 1, level_base = 0, depth = 0;
-        uint32_t *cur = level_a.p, *nxt = level_b.p;
+        uint32_t *cur = level_a, *nxt = level_b;
         // (the root of a scene with <= MAX_LEAF primitives would be a leaf: such scenes never come here)
         while (n_level) {
             depth++;
             const int g = (int)((n_level + TPB - 1) / TPB);
-            level_count_kernel<<<g, TPB>>>(tv, cur, n_level, counts.p);
+            level_count_kernel<<<g, TPB>>>(tv, cur, n_level, counts);
             CUB_OK(cudaGetLastError());
             size_t sb = tmp_bytes;
-            CUB_OK(cub::DeviceScan::ExclusiveSum(cub_tmp.p, sb, counts.p, offsets.p, (int)n_level));
+            CUB_OK(cub::DeviceScan::ExclusiveSum(cub_tmp, sb, counts, offsets, (int)n_level));
             const uint32_t next_base = level_base + n_level;
-            level_emit_kernel<<<g, TPB>>>(tv, cur, n_level, level_base, offsets.p, next_base, nodes_tmp.p, nxt);
+            level_emit_kernel<<<g, TPB>>>(tv, cur, n_level, level_base, offsets, next_base, nodes_tmp, nxt);
             CUB_OK(cudaGetLastError());
             uint32_t last_off = 0, last_cnt = 0;
-            CUB_OK(cudaMemcpy(&last_off, offsets.p + (n_level - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
-            CUB_OK(cudaMemcpy(&last_cnt, counts.p + (n_level - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            CUB_OK(cudaMemcpy(&last_off, offsets + (n_level - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            CUB_OK(cudaMemcpy(&last_cnt, counts + (n_level - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
             level_base = next_base;
             n_level = last_off + last_cnt;
             std::swap(cur, nxt);
@@ -513,15 +512,14 @@ int build_scene_on_device(const rt_scene_desc *d, const std::vector<unsigned cha
         stage("collapse to BVH4");
         // ---- 6. final arrays
         CUB_OK(cudaMalloc((void **)&d_nodes, (size_t)out.n_nodes * 128));
-        CUB_OK(cudaMemcpy(d_nodes, nodes_tmp.p, (size_t)out.n_nodes * 128, cudaMemcpyDeviceToDevice));
+        CUB_OK(cudaMemcpy(d_nodes, nodes_tmp, (size_t)out.n_nodes * 128, cudaMemcpyDeviceToDevice));
         CUB_OK(cudaMalloc((void **)&d_prims, (size_t)n * 64));
         CUB_OK(cudaMalloc((void **)&d_shade, (size_t)n * 16));
-        CUB_OK(d_nan.alloc(2));
-        CUB_OK(cudaMemset(d_nan.p, 0xFF, 2 * sizeof(unsigned long long)));
-        records_kernel<<<grid_n, TPB>>>(d_sph.p, d_tri.p, ns, n, vals_out.p, d_tm.p, d_prims, d_shade, d_nan.p, d_nan.p + 1);
+        CUB_OK(cudaMemset(d_nan, 0xFF, 2 * sizeof(unsigned long long)));
+        records_kernel<<<grid_n, TPB>>>(d_sph, d_tri, ns, n, vals_out, d_tm, d_prims, d_shade, d_nan, d_nan + 1);
         CUB_OK(cudaGetLastError());
         unsigned long long hn[2];
-        CUB_OK(cudaMemcpy(hn, d_nan.p, sizeof(hn), cudaMemcpyDeviceToHost));
+        CUB_OK(cudaMemcpy(hn, d_nan, sizeof(hn), cudaMemcpyDeviceToHost));
         out.nan_hit_slot = hn[0] == ~0ull ? -1 : (int32_t)(hn[0] & 0xFFFFFFFFu);
         out.nan_hit_slot_culled = hn[1] == ~0ull ? -1 : (int32_t)(hn[1] & 0xFFFFFFFFu);
         out.n_slots = n;
