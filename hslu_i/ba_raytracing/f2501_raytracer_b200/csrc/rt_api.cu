@@ -328,8 +328,13 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         const bool defer = beams && units_per_warp < defer_below;
         // Chained records between the light groups of a batch (direct_kernel): windows of `chain_window` batches with
         // two generations each; the DEFER variant keeps one window with every generation.
-        uint32_t chain_window = 16384;
-        if (const char *e = getenv("RT_CHAIN_WINDOW")) chain_window = (uint32_t)std::max(1, atoi(e));  // tests: tiny windows
+        // The window must be several times the number of resident warps: a unit's predecessor was handed out one window
+        // earlier, and only if (nearly) all of it has been worked off by then does the unit find its record waiting
+        // (measured on B200, profiles/README.md: 16384 batches = 4 x the resident warps costs 8 % of the frame in waits,
+        // 65536 nothing).
+        uint32_t chain_window = 65536;
+        if (const char *e = getenv("RT_CHAIN_WINDOW")) chain_window = (uint32_t)std::max(1, atoi(e));  // A/B runs, tests
+        chain_window = std::max(chain_window, 2u * resident_warps);  // (below: one working warp per batch column, the rest waiting)
         chain_window = defer ? warps_needed : std::min(chain_window, warps_needed);
         const uint32_t n_windows = (warps_needed + chain_window - 1) / chain_window;
         const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;

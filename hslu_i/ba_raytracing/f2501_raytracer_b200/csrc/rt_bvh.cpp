@@ -294,7 +294,11 @@ void pack_materials_and_lights(const rt_scene_desc *d, FlatScene &out, std::vect
         float *o = &out.mats[12 * (size_t)i];
         o[0] = m.color[0]; o[1] = m.color[1]; o[2] = m.color[2]; o[3] = m.metallic;
         o[4] = m.shininess; o[5] = m.ior; o[6] = m.opacity; o[7] = m.boost;
-        o[8] = u2f(m.has_opacity ? 1u : 0u); o[9] = u2f(tm ? 1u : 0u); o[10] = 0; o[11] = 0;
+        // compute_fresnel against air-like surroundings (other_ior = 1.0: every shadow / transmittance query,
+        // raytracer.rs:60): its two divisions depend on the material alone -- evaluated here once, in f32, the same
+        // IEEE operations (material.rs:480-500)
+        const float f0r = (1.0f - m.ior) / (1.0f + m.ior);
+        o[8] = u2f(m.has_opacity ? 1u : 0u); o[9] = u2f(tm ? 1u : 0u); o[10] = f0r * f0r; o[11] = 1.0f / m.ior;
     }
     out.lights.resize(8 * (size_t)d->n_lights);
     for (uint32_t i = 0; i < d->n_lights; i++) {

@@ -50,7 +50,7 @@ struct FlatScene {
     std::vector<float> nodes;    // 32 floats per node
     std::vector<float> prims;    // 16 floats per primitive slot
     std::vector<float> shade_n;  // 4 floats per slot: stored triangle normal (spheres: 0)
-    std::vector<float> mats;     // 12 floats per material: (color, metallic) (shininess, ior, opacity, boost) (bits has_opacity, bits transmissive, 0, 0)
+    std::vector<float> mats;     // 12 floats per material: (color, metallic) (shininess, ior, opacity, boost) (bits has_opacity, bits transmissive, f0 against ior 1.0, 1 / ior)
     std::vector<float> lights;   // 8 floats per light: (pos, intensity) (color, 0)
     uint32_t n_nodes = 0, n_prims = 0, n_mats = 0, n_lights = 0;  // n_prims counts slots (references)
     uint32_t root_ref = CHILD_EMPTY;  // child reference of the root (a leaf ref for tiny scenes)

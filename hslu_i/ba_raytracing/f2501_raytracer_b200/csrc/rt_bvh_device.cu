@@ -98,9 +98,19 @@ __global__ void bounds_kernel(const rt_sphere *sph, const rt_triangle *tri, uint
         prim_box(sph, tri, ns, i, l, h);
         const uint32_t mat = i < ns ? sph[i].material : tri[i - ns].material;
         bad_m |= mat >= n_materials;
+        // NaN or infinite coordinates (fminf / fmaxf drop a NaN operand, so the raw values are looked at)
+        float sum = 0.0f;
+        if (i < ns) {
+            sum = ((sph[i].center[0] + sph[i].center[1]) + sph[i].center[2]) + sph[i].radius;
+        } else {
+            const rt_triangle *t = tri + (i - ns);
+#pragma unroll
+            for (int k = 0; k < 3; k++) sum += (fabsf(t->v1[k]) + fabsf(t->v2[k])) + fabsf(t->v3[k]);
+        }
+        bad_c |= !(sum - sum == 0.0f);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            bad_c |= !(l[k] - l[k] == 0.0f) || !(h[k] - h[k] == 0.0f);  // NaN or infinite
+            bad_c |= !(l[k] - l[k] == 0.0f) || !(h[k] - h[k] == 0.0f);
             lo[k] = fminf(lo[k], l[k]);
             hi[k] = fmaxf(hi[k], h[k]);
         }

@@ -169,36 +169,40 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     // sitting on the surface) they are taken without nvcc's per-call range checks (rt_device.cuh).
     const float3 l2p = lpos - hp;
     const float d2 = dot3(l2p, l2p);
+    const bool d2_ok = (d2 > 1e-30f) & (d2 < 1e30f);  // inside the range of the sequences above (false for NaN)
     float3 ldir = l2p * rcp_rn_normal(sqrt_rn_normal(d2));
-    float3 q = hp + ldir * p.eps_d;
-    const float3 lq = lpos - q;
-    const float m2 = dot3(lq, lq);
-    float maxd = sqrt_rn_normal(m2);
-    float3 d = ldir * rcp_rn_normal(sqrt_rn_normal(dot3(ldir, ldir)));
-    if (!((d2 > 1e-30f) & (d2 < 1e30f) & (m2 > 1e-30f))) {  // outside the range of the sequences above, or NaN
-        ldir = normalized3(l2p);
-        q = hp + ldir * p.eps_d;
-        maxd = mag3(lpos - q);
-        d = normalized3(ldir);
-    }
+    if (!d2_ok) ldir = normalized3(l2p);
     ShadowResult sh;
-#if RT_EMPTY_LIST_SKIP
-    // an empty candidate list: the query is "nothing on the segment" whatever the ray -- the whole
-    // warp skips the list walk when none of its lanes has a candidate
-    if (MODE == 1 && n_cand == 0 && *last_occluder < 0) {
+    sh.occluded = false;
+    sh.opacity = 1.0f;
+    sh.filter = splat(1.0f);
+    // An empty candidate list (and no occluder remembered from an earlier copy): the query is "nothing on the
+    // segment" whatever the ray, so the ray itself -- origin offset, length, second normalisation: two of the three
+    // square roots -- is not built at all.
+    const bool nothing_to_test = RT_EMPTY_LIST_SKIP && MODE == 1 && n_cand == 0 && *last_occluder < 0;
+    if (nothing_to_test) {
         if (COUNT) cn.shadow++;
-        sh.occluded = false;
-        sh.opacity = 1.0f;
-        sh.filter = splat(1.0f);
-    } else
-#endif
-    if (MODE == 1)
-        sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, d, maxd, cull, cn)
-                         : trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
-    else if (MODE == 2)
-        sh = trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
-    else
-        sh = trace_shadow<COUNT>(sc, q, d, maxd, cull, cn);
+    } else {
+        const float3 q = hp + ldir * p.eps_d;
+        const float3 lq = lpos - q;
+        const float m2 = dot3(lq, lq);
+        float maxd;
+        float3 d;
+        if (d2_ok & (m2 > 1e-30f)) {
+            maxd = sqrt_rn_normal(m2);
+            d = ldir * rcp_rn_normal(sqrt_rn_normal(dot3(ldir, ldir)));
+        } else {
+            maxd = mag3(lq);
+            d = normalized3(ldir);
+        }
+        if (MODE == 1)
+            sh = n_cand >= 0 ? trace_shadow_list<COUNT>(sc, cand, n_cand, *last_occluder, q, d, maxd, cull, cn)
+                             : trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
+        else if (MODE == 2)
+            sh = trace_shadow_outlined<COUNT>(sc, q, d, maxd, cull, &cn);
+        else
+            sh = trace_shadow<COUNT>(sc, q, d, maxd, cull, cn);
+    }
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
     const float diffuse = smax(dot3(hn, ldir), 0.0f);
@@ -909,13 +913,15 @@ RT_DEV unsigned long long dbg_globaltimer() {
 constexpr uint32_t HEAVY_CAP = 16384;             // most deferred units per launch (RenderParams::heavy_cap; beyond: processed in place)
 constexpr uint32_t CHAIN_DEFERRED = 0x80000000u;  // flag in a chain tag: the unit is on the heavy list
 struct HeavyQueue {
-    unsigned int n_heavy;       // units on the list
-    unsigned int next_task;     // next sub-task ticket: heavy index * M + copy
+    unsigned int n_heavy;       // list slots handed out (a unit reserves its own slot and those of its successors at once)
     unsigned int warps_done_a;  // warps that have left the unit loop (after that the list is final)
+    unsigned int next_task;     // next sub-task ticket: position in `ready` * M + copy   } read together (8-byte aligned)
+    unsigned int n_ready;       // units whose slot has been published, in publication order }
     unsigned int unit_counter;  // direct_kernel's unit queue (here so that one memset resets everything)
-    unsigned int pad[4];
-    unsigned int done[HEAVY_CAP];  // finished sub-tasks
-    unsigned int unit[HEAVY_CAP];  // unit + 1; 0 until written
+    unsigned int pad[3];
+    unsigned int done[HEAVY_CAP];   // finished sub-tasks per slot
+    unsigned int unit[HEAVY_CAP];   // per slot: unit + 1; 0 until written
+    unsigned int ready[HEAVY_CAP];  // publication order: slot + 1; 0 until written
 };
 RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
 // Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render /
@@ -1020,7 +1026,8 @@ RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float
 // that it does not weigh on the register allocation of the unit loop.
 template <bool COUNT, bool POINTS>
 __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
-                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog) {
+                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog, bool final_phase,
+                                                uint32_t max_tasks) {
     const RenderParams &p = *gp;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -1029,33 +1036,39 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const size_t chain_stride = (size_t)n_batches * 32u;
     Counters cn = {0, 0, 0, 0, 0, 0};
-    if (lane == 0) atomicAdd(&hq->warps_done_a, 1u);
-    for (;;) {
-        // tickets are handed out in list order; one that is ahead of the list waits until the list has grown
-        // that far or is final (every warp has left the unit loop)
+    // final_phase: the unit queue has run dry for this warp -- it works sub-tasks off until the list is final (every warp
+    // has left the unit loop) and empty.  Otherwise (a warp lending a hand between two units): at most `max_tasks`
+    // sub-tasks, and only ones that are ready right now.  A ticket is only ever taken for a published unit (CAS), so no
+    // warp waits for a unit that is listed later -- or never.
+    if (final_phase && lane == 0) {
+        __threadfence();  // this warp's publications before its "left the unit loop"
+        atomicAdd(&hq->warps_done_a, 1u);
+    }
+    for (uint32_t taken = 0; final_phase || taken < max_tasks; taken++) {
         uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0;
         if (lane == 0) {
-            const unsigned int t = atomicAdd(&hq->next_task, 1u);
-            const uint32_t want = t / p.M;
             for (uint32_t spins = 0;; spins++) {
                 if (spins > WAIT_SLEEPS) {
                     watchdog_trip(watchdog, 1u);
                     break;
                 }
                 const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
-                const unsigned int n = ld_volatile_u32(&hq->n_heavy);  // (never above heavy_cap: slots are reserved by CAS)
-                if (want < n) {
-                    idx = want;
-                    c = t - want * p.M;
-                    for (uint32_t w = 0; (unit = ld_volatile_u32(&hq->unit[idx]) - 1u) == 0xFFFFFFFFu; w++)
-                        if (w > WAIT_SPINS) {
+                __threadfence();  // (the flag first, then the counters: a final list has all its entries counted)
+                const unsigned int t = ld_volatile_u32(&hq->next_task), n = ld_volatile_u32(&hq->n_ready);
+                if (t / p.M < n) {
+                    if (atomicCAS(&hq->next_task, t, t + 1u) != t) continue;  // somebody else took it: look again
+                    const uint32_t pos = t / p.M;
+                    c = t - pos * p.M;
+                    uint32_t w = 0;
+                    while ((idx = ld_volatile_u32(&hq->ready[pos]) - 1u) == 0xFFFFFFFFu)  // (counted, being written)
+                        if (++w > WAIT_SPINS) {
                             watchdog_trip(watchdog, 2u);
-                            idx = 0xFFFFFFFFu;
                             break;
                         }
+                    if (idx != 0xFFFFFFFFu) unit = ld_volatile_u32(&hq->unit[idx]) - 1u;  // (written before the slot was counted)
                     break;
                 }
-                if (final_list) break;
+                if (!final_phase || final_list) break;
                 __nanosleep(1000);
             }
         }
@@ -1136,7 +1149,12 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
     if (zero_sample) *sample = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     __threadfence();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) *(volatile unsigned int *)&hq->unit[idx] = unit + 1u;
+    if ((threadIdx.x & 31) == 0) {
+        *(volatile unsigned int *)&hq->unit[idx] = unit + 1u;
+        __threadfence();
+        const unsigned int r = atomicAdd(&hq->n_ready, 1u);  // sub-task tickets follow the publication order
+        *(volatile unsigned int *)&hq->ready[r] = idx + 1u;
+    }
 }
 
 // DEFER: with the deferral of very expensive units compiled in.  It costs a few per cent of steady-state
@@ -1162,6 +1180,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
     Counters cn = {0, 0, 0, 0, 0, 0};
+    uint32_t units_done = 0;
 #ifdef RT_DBG_TAIL
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long dbg_t0 = dbg_globaltimer(), dbg_spin = 0, dbg_last_start = 0, dbg_worst = 0, dbg_worst_info = 0, dbg_cur_info = 0;
@@ -1169,6 +1188,18 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     uint32_t dbg_units = 0, dbg_helped = 0;
 #endif
     for (;;) {
+        if (DEFER && BEAM && deferring && (++units_done & 7u) == 0u) {
+            // every 8th unit: are there deferred sub-tasks waiting?  Then do two of them now -- a deferred unit is worked
+            // off by many warps soon after it was listed instead of at the end of the launch, which is what is left of
+            // the tail of a small launch.  (One 8-byte load; the helper takes only tickets that are ready.)
+            unsigned int waiting = 0;
+            if (lane == 0) {
+                const unsigned long long v = *(const volatile unsigned long long *)&hq->next_task;  // (next_task, n_ready)
+                waiting = (unsigned int)(v & 0xFFFFFFFFull) / p.M < (unsigned int)(v >> 32);
+            }
+            if (__shfl_sync(FULL, waiting, 0))
+                finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, 0u, COUNT ? &cn : nullptr, watchdog, false, 2u);
+        }
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
         unit = __shfl_sync(FULL, unit, 0);
@@ -1196,11 +1227,13 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             // batch -- and with it, through the chain, every reader of those slots -- has finished
             const unsigned int want_done = tag_base - 1u;  // = tag of (win - 1, last group)
             if (lane == 0) {
-                for (uint32_t spins = 0; ld_acquire_gpu_u32(p.chain_done + b_in_win) != want_done; spins++)
+                for (uint32_t spins = 0; ld_acquire_gpu_u32(p.chain_done + b_in_win) != want_done; spins++) {
                     if (spins > WAIT_SPINS) {
                         watchdog_trip(watchdog, 6u);
                         break;
                     }
+                    __nanosleep(200);
+                }
             }
             __syncwarp();
         }
@@ -1230,6 +1263,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                         watchdog_trip(watchdog, 4u);
                         break;
                     }
+                    if (spins > 4u) __nanosleep(200);  // (a waiting warp must not take issue slots from the working ones)
                     sd = ld_relaxed_gpu(&prev_rec->d);
                     ss = ld_relaxed_gpu(&prev_rec->s);
                     const uint32_t td = __float_as_uint(sd.w), ts = __float_as_uint(ss.w);
@@ -1355,7 +1389,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
+        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog, true,
+                                          0u);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif

@@ -518,16 +518,18 @@ def test_deferred_units_are_bit_identical(pkg, scenes, monkeypatch):
         assert np.array_equal(a.buffer, c.buffer) and np.array_equal(a.hit_mask, c.hit_mask)
 
 
-@pytest.mark.parametrize("window", ["3", "64", "1000"])
+@pytest.mark.parametrize("window", ["8192", "11000", "30000"])
 def test_chained_records_live_in_a_bounded_window(pkg, scenes, monkeypatch, window):
     """direct_kernel chains the running light sums of a batch from light group to light group through records in
-    global memory.  The records live in a window of RT_CHAIN_WINDOW batches x 2 generations (default 16384 batches =
-    32 MB for any frame size); a slot is reused by the next window only after the previous window's last unit of that
-    batch has published its tag.  Tiny windows make every unit take that path: same image bit for bit, no watchdog."""
+    global memory.  The records live in a window of RT_CHAIN_WINDOW batches x 2 generations (default 65536 batches =
+    128 MB for any frame size; never below twice the resident warps); a slot is reused by the next window only after
+    the previous window's last unit of that batch has published its tag.  Several (also ragged) windows per frame:
+    same image bit for bit, no watchdog, also in the frame after."""
     feat = "high_quality,simd_render"
     flat, dev = scenes("semesterbild", feat)
-    rc = pkg.RenderConfig.from_features(feat, 2, width=384, height=320, n_light_clouds=512)
+    rc = pkg.RenderConfig.from_features(feat, 2, width=384, height=320, n_light_clouds=512)   # 61440 batches of 32 samples
     monkeypatch.setenv("RT_DEFER_BELOW", "0")      # the variant that windows its records
+    monkeypatch.setenv("RT_CHAIN_WINDOW", "1000000")   # one window
     ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
     monkeypatch.setenv("RT_CHAIN_WINDOW", window)
     for _ in range(2):                             # (twice: the second frame finds the first one's tags in the slots)
