@@ -1027,7 +1027,7 @@ RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float
 template <bool COUNT, bool POINTS>
 __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
                                                 uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog, bool final_phase,
-                                                uint32_t max_tasks) {
+                                                uint32_t max_tasks, uint32_t *pending) {
     const RenderParams &p = *gp;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -1038,27 +1038,30 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
     Counters cn = {0, 0, 0, 0, 0, 0};
     // final_phase: the unit queue has run dry for this warp -- it works sub-tasks off until the list is final (every warp
     // has left the unit loop) and empty.  Otherwise (a warp lending a hand between two units): at most `max_tasks`
-    // sub-tasks, and only ones that are ready right now.  A ticket is only ever taken for a published unit (CAS), so no
-    // warp waits for a unit that is listed later -- or never.
+    // sub-tasks, and only ones that are ready right now.  Tickets come from one atomicAdd each (no compare-and-swap
+    // loops: thousands of warps ask at the same moment).  A helping warp only asks when a sub-task looks ready; should
+    // another warp have been quicker, its ticket refers to a unit that is not listed yet -- it keeps the ticket
+    // (`*pending`), goes back to its units and looks again at the next opportunity, at the latest in its final phase.
     if (final_phase && lane == 0) {
         __threadfence();  // this warp's publications before its "left the unit loop"
         atomicAdd(&hq->warps_done_a, 1u);
     }
     for (uint32_t taken = 0; final_phase || taken < max_tasks; taken++) {
-        uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0;
+        uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0, ticket = *pending;
         if (lane == 0) {
-            for (uint32_t spins = 0;; spins++) {
+            if (ticket == 0xFFFFFFFFu && (final_phase || ld_volatile_u32(&hq->next_task) / p.M < ld_volatile_u32(&hq->n_ready)))
+                ticket = atomicAdd(&hq->next_task, 1u);
+            for (uint32_t spins = 0; ticket != 0xFFFFFFFFu; spins++) {
                 if (spins > WAIT_SLEEPS) {
                     watchdog_trip(watchdog, 1u);
+                    ticket = 0xFFFFFFFFu;
                     break;
                 }
-                const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
-                __threadfence();  // (the flag first, then the counters: a final list has all its entries counted)
-                const unsigned int t = ld_volatile_u32(&hq->next_task), n = ld_volatile_u32(&hq->n_ready);
-                if (t / p.M < n) {
-                    if (atomicCAS(&hq->next_task, t, t + 1u) != t) continue;  // somebody else took it: look again
-                    const uint32_t pos = t / p.M;
-                    c = t - pos * p.M;
+                const bool final_list = final_phase && ld_volatile_u32(&hq->warps_done_a) >= total_warps;
+                if (final_list) __threadfence();  // (the flag first, then the counter: a final list has all its entries counted)
+                const uint32_t pos = ticket / p.M;
+                if (pos < ld_volatile_u32(&hq->n_ready)) {
+                    c = ticket - pos * p.M;
                     uint32_t w = 0;
                     while ((idx = ld_volatile_u32(&hq->ready[pos]) - 1u) == 0xFFFFFFFFu)  // (counted, being written)
                         if (++w > WAIT_SPINS) {
@@ -1066,12 +1069,19 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                             break;
                         }
                     if (idx != 0xFFFFFFFFu) unit = ld_volatile_u32(&hq->unit[idx]) - 1u;  // (written before the slot was counted)
+                    ticket = 0xFFFFFFFFu;  // used
                     break;
                 }
-                if (!final_phase || final_list) break;
+                if (!final_phase) break;   // not listed yet: keep the ticket for later
+                if (final_list) {          // never will be: the launch has no such sub-task
+                    ticket = 0xFFFFFFFFu;
+                    break;
+                }
                 __nanosleep(1000);
             }
         }
+        ticket = __shfl_sync(FULL, ticket, 0);
+        *pending = ticket;
         idx = __shfl_sync(FULL, idx, 0);
         if (idx == 0xFFFFFFFFu) break;
         c = __shfl_sync(FULL, c, 0);
@@ -1160,6 +1170,12 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
 // DEFER: with the deferral of very expensive units compiled in.  It costs a few per cent of steady-state
 // throughput (register pressure in the unit loop) and removes the tail of the launch, so the host selects
 // it when a launch has few units per warp -- a rank's share of a multi-GPU frame.
+#ifndef RT_HEAVY_HELP_EVERY
+#define RT_HEAVY_HELP_EVERY 8  // a warp looks for deferred sub-tasks every this many units (0: only at the end of the launch)
+#endif
+#ifndef RT_WAIT_BACKOFF_NS
+#define RT_WAIT_BACKOFF_NS 200  // sleep between two polls of a chained record that is not there yet (0: plain polling)
+#endif
 #ifndef RT_DEFER_MIN_CTAS
 #define RT_DEFER_MIN_CTAS 6  // the DEFER variant is better off with 80 registers (measured: -2.3 % on a rank's eighth of C3)
 #endif
@@ -1180,7 +1196,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
     Counters cn = {0, 0, 0, 0, 0, 0};
-    uint32_t units_done = 0;
+    uint32_t units_done = 0, pending_ticket = 0xFFFFFFFFu;  // (DEFER: a sub-task ticket taken while helping, not ready yet)
 #ifdef RT_DBG_TAIL
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long dbg_t0 = dbg_globaltimer(), dbg_spin = 0, dbg_last_start = 0, dbg_worst = 0, dbg_worst_info = 0, dbg_cur_info = 0;
@@ -1188,17 +1204,18 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     uint32_t dbg_units = 0, dbg_helped = 0;
 #endif
     for (;;) {
-        if (DEFER && BEAM && deferring && (++units_done & 7u) == 0u) {
+        if (RT_HEAVY_HELP_EVERY > 0 && DEFER && BEAM && deferring && (++units_done % (uint32_t)(RT_HEAVY_HELP_EVERY > 0 ? RT_HEAVY_HELP_EVERY : 1)) == 0u) {
             // every 8th unit: are there deferred sub-tasks waiting?  Then do two of them now -- a deferred unit is worked
             // off by many warps soon after it was listed instead of at the end of the launch, which is what is left of
             // the tail of a small launch.  (One 8-byte load; the helper takes only tickets that are ready.)
             unsigned int waiting = 0;
             if (lane == 0) {
                 const unsigned long long v = *(const volatile unsigned long long *)&hq->next_task;  // (next_task, n_ready)
-                waiting = (unsigned int)(v & 0xFFFFFFFFull) / p.M < (unsigned int)(v >> 32);
+                const unsigned int first_free = pending_ticket != 0xFFFFFFFFu ? pending_ticket : (unsigned int)(v & 0xFFFFFFFFull);
+                waiting = first_free / p.M < (unsigned int)(v >> 32);
             }
             if (__shfl_sync(FULL, waiting, 0))
-                finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, 0u, COUNT ? &cn : nullptr, watchdog, false, 2u);
+                finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, 0u, COUNT ? &cn : nullptr, watchdog, false, 2u, &pending_ticket);
         }
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
@@ -1222,12 +1239,16 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         DirectState *const own_rec = state + (size_t)gen * chain_stride + (size_t)b_in_win * 32u + lane;
         const DirectState *const prev_rec = state + (size_t)prev_gen * chain_stride + (size_t)b_in_win * 32u + lane;  // (only dereferenced when group_index > 0)
         const uint32_t tag_base = frame_tag + win * n_groups;  // tags are unique per (frame, window, group)
-        if (!DEFER && win > 0 && group_index == 0 && n_groups > 1) {
-            // this unit's records reuse the slots of the previous window: wait until that window's last unit of this
-            // batch -- and with it, through the chain, every reader of those slots -- has finished
+        if (!DEFER && win > 0 && (group_index == 0 || last) && n_groups > 1) {
+            // The FIRST unit of a batch column in a window: its records reuse the slots of the previous window -- wait
+            // until that window's last unit of this column, and with it (through the chain) every reader of those slots,
+            // has finished.  The LAST unit waits for the same tag before it publishes its own: lanes without a hit take no
+            // part in the record chain, so a last unit none of whose lanes hit would otherwise publish at once -- ahead
+            // of the previous window's tag, which the first unit of its own window may still be waiting for.  Tags only
+            // grow (per window, per frame), so "reached" is a signed comparison.
             const unsigned int want_done = tag_base - 1u;  // = tag of (win - 1, last group)
             if (lane == 0) {
-                for (uint32_t spins = 0; ld_acquire_gpu_u32(p.chain_done + b_in_win) != want_done; spins++) {
+                for (uint32_t spins = 0; (int32_t)(ld_acquire_gpu_u32(p.chain_done + b_in_win) - want_done) < 0; spins++) {
                     if (spins > WAIT_SPINS) {
                         watchdog_trip(watchdog, 6u);
                         break;
@@ -1263,7 +1284,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                         watchdog_trip(watchdog, 4u);
                         break;
                     }
-                    if (spins > 4u) __nanosleep(200);  // (a waiting warp must not take issue slots from the working ones)
+                    if (RT_WAIT_BACKOFF_NS > 0 && spins > 4u) __nanosleep(RT_WAIT_BACKOFF_NS);  // (a waiting warp must not take issue slots from the working ones)
                     sd = ld_relaxed_gpu(&prev_rec->d);
                     ss = ld_relaxed_gpu(&prev_rec->s);
                     const uint32_t td = __float_as_uint(sd.w), ts = __float_as_uint(ss.w);
@@ -1390,7 +1411,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
         finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog, true,
-                                          0u);
+                                          0u, &pending_ticket);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif

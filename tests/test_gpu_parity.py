@@ -733,8 +733,9 @@ def test_progressive_render_overlaps_copy_and_callback_with_the_next_band(pkg, s
         slept.append(time.perf_counter() - t)
 
     dev.render_progressive(rc, None, band_rows=64)   # (first use allocates the pinned band buffers and the copy stream)
+    _, st_quiet = dev.render_progressive(rc, None, band_rows=64)
     prog, st = dev.render_progressive(rc, None, band_rows=64, on_band=on_band)
     assert np.array_equal(prog.buffer, full.buffer) and np.array_equal(prog.hit_mask, full.hit_mask)
     assert len(slept) == 10 and st["overlapped_bands"] >= 7
-    # the callbacks' time hides behind the GPU: the whole call costs less than frame + callbacks back to back
-    assert st["total_ms"] < st_full["total_ms"] + 1e3 * sum(slept) + 2.0
+    # the callbacks' time hides behind the GPU: ten callbacks of 0.5 ms cost the call far less than their 5 ms
+    assert st["total_ms"] < st_quiet["total_ms"] + 0.6 * 1e3 * sum(slept) + 1.0
