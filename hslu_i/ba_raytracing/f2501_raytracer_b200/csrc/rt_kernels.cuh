@@ -921,7 +921,8 @@ struct HeavyQueue {
     unsigned int pad[3];
     unsigned int done[HEAVY_CAP];   // finished sub-tasks per slot
     unsigned int unit[HEAVY_CAP];   // per slot: unit + 1; 0 until written
-    unsigned int ready[HEAVY_CAP];  // publication order: slot + 1; 0 until written
+    unsigned int ready[HEAVY_CAP];  // publication order of the units that are worked off as sub-tasks: slot + 1; 0 until written
+    unsigned int claim[HEAVY_CAP];  // per slot: 1 once a warp has taken over the slot's final sums (exactly one does)
 };
 RT_DEV unsigned int ld_volatile_u32(const unsigned int *p) { return *(const volatile unsigned int *)p; }
 // Every wait loop of direct_kernel is bounded: a protocol error must surface as an error code (rt_render /
@@ -1022,12 +1023,71 @@ RT_DEV void store_direct_sample(const RenderParams &p, const SampleRec &r, float
     }
 }
 
+// The final sums of a listed unit (slot idx = light group g of batch b): the predecessor's sums continued with the unit's
+// M per-copy contributions from the scratch slab, in copy order -- the reference's light order -- then the unit's own
+// record (or, for the last group, the sample).  NEVER blocks: if the predecessor's record is not final yet, the call
+// returns, and the warp that finishes the predecessor carries on into this slot (it looks at done[idx + 1] after it has
+// written its record; this call looked at the record after done[idx] was complete: with a fence on both sides at least
+// one of the two sees the other).  `claim` makes sure exactly one warp does a slot.  After a slot the same warp goes on to
+// the next group's slot if that one's contributions are complete -- a chain of listed units is finished by whoever
+// completes its last missing piece, at once, instead of by waiting warps.
+template <bool POINTS>
+__device__ __noinline__ void finish_chain(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups, uint32_t frame_tag,
+                                          uint32_t idx, uint32_t g, uint32_t b) {
+    const RenderParams &p = *gp;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t FULL = 0xFFFFFFFFu;
+    const uint32_t n_batches = (p.n_items + 31u) / 32u;
+    const size_t chain_stride = (size_t)n_batches * 32u;
+    const uint32_t item = b * 32u + lane;
+    const SampleRec r = rebuild_sample<POINTS>(p, item);
+    float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
+    bool ready = true;
+    if (g > 0 && r.hit) {
+        const uint32_t want = frame_tag + g - 1u;
+        const float4 sd = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].d), ss = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].s);
+        ready = __float_as_uint(sd.w) == want && __float_as_uint(ss.w) == want;
+        sum_d = f3(sd.x, sd.y, sd.z);
+        sum_s = f3(ss.x, ss.y, ss.z);
+    }
+    if (!__all_sync(FULL, ready)) return;  // the predecessor's finisher will come here
+    unsigned int won = 0;
+    if (lane == 0) won = atomicCAS(&hq->claim[idx], 0u, 1u) == 0u;
+    if (!__shfl_sync(FULL, won, 0)) return;
+    for (;;) {
+        if (r.hit) {
+            const float4 *slab = hscratch + ((size_t)idx * p.M * 32u + lane) * 2u;  // + copy * 64
+            for (uint32_t k = 0; k < p.M; k++) {
+                const float4 a = ld_relaxed_gpu(slab + (size_t)k * 64u), b2 = ld_relaxed_gpu(slab + (size_t)k * 64u + 1);
+                sum_d = sum_d + f3(a.x, a.y, a.z);
+                sum_s = sum_s + f3(b2.x, b2.y, b2.z);
+            }
+            if (g + 1 != n_groups) {
+                const float tag = __uint_as_float(frame_tag + g);
+                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+            } else {
+                store_direct_sample<POINTS>(p, r, sum_d, sum_s);
+            }
+        }
+        if (g + 1 == n_groups) return;
+        // the next group's slot was reserved together with this one: are its contributions complete?
+        __threadfence();
+        __syncwarp();
+        won = 0;
+        if (lane == 0) won = ld_volatile_u32(&hq->done[idx + 1u]) == p.M && atomicCAS(&hq->claim[idx + 1u], 0u, 1u) == 0u;
+        if (!__shfl_sync(FULL, won, 0)) return;
+        __threadfence();
+        idx++;
+        g++;
+    }
+}
+
 // Phase B of direct_kernel (see above).  Out of line, parameters read from their global-memory copy, so
 // that it does not weigh on the register allocation of the unit loop.
 template <bool COUNT, bool POINTS>
 __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQueue *hq, float4 *hscratch, DirectState *state, uint32_t n_groups,
-                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog, bool final_phase,
-                                                uint32_t max_tasks, uint32_t *pending) {
+                                                uint32_t frame_tag, uint32_t total_warps, Counters *cn_out, unsigned int *watchdog) {
     const RenderParams &p = *gp;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t FULL = 0xFFFFFFFFu;
@@ -1036,30 +1096,26 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const size_t chain_stride = (size_t)n_batches * 32u;
     Counters cn = {0, 0, 0, 0, 0, 0};
-    // final_phase: the unit queue has run dry for this warp -- it works sub-tasks off until the list is final (every warp
-    // has left the unit loop) and empty.  Otherwise (a warp lending a hand between two units): at most `max_tasks`
-    // sub-tasks, and only ones that are ready right now.  Tickets come from one atomicAdd each (no compare-and-swap
-    // loops: thousands of warps ask at the same moment).  A helping warp only asks when a sub-task looks ready; should
-    // another warp have been quicker, its ticket refers to a unit that is not listed yet -- it keeps the ticket
-    // (`*pending`), goes back to its units and looks again at the next opportunity, at the latest in its final phase.
-    if (final_phase && lane == 0) {
+    // The unit queue has run dry for this warp: it works sub-tasks off until the list is final (every warp has left the
+    // unit loop) and empty.  Tickets come from one atomicAdd each and follow the PUBLICATION order of the units
+    // (`ready[]`), so a ticket never refers to a unit that is listed later.  (Measured and dropped, profiles/README.md:
+    // warps lending a hand between two units as soon as a unit is listed -- +2 % on a rank's eighth of the headline frame.)
+    if (lane == 0) {
         __threadfence();  // this warp's publications before its "left the unit loop"
         atomicAdd(&hq->warps_done_a, 1u);
     }
-    for (uint32_t taken = 0; final_phase || taken < max_tasks; taken++) {
-        uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0, ticket = *pending;
+    for (;;) {
+        uint32_t idx = 0xFFFFFFFFu, c = 0, unit = 0;
         if (lane == 0) {
-            if (ticket == 0xFFFFFFFFu && (final_phase || ld_volatile_u32(&hq->next_task) / p.M < ld_volatile_u32(&hq->n_ready)))
-                ticket = atomicAdd(&hq->next_task, 1u);
-            for (uint32_t spins = 0; ticket != 0xFFFFFFFFu; spins++) {
+            const unsigned int ticket = atomicAdd(&hq->next_task, 1u);
+            const uint32_t pos = ticket / p.M;
+            for (uint32_t spins = 0;; spins++) {
                 if (spins > WAIT_SLEEPS) {
                     watchdog_trip(watchdog, 1u);
-                    ticket = 0xFFFFFFFFu;
                     break;
                 }
-                const bool final_list = final_phase && ld_volatile_u32(&hq->warps_done_a) >= total_warps;
+                const bool final_list = ld_volatile_u32(&hq->warps_done_a) >= total_warps;
                 if (final_list) __threadfence();  // (the flag first, then the counter: a final list has all its entries counted)
-                const uint32_t pos = ticket / p.M;
                 if (pos < ld_volatile_u32(&hq->n_ready)) {
                     c = ticket - pos * p.M;
                     uint32_t w = 0;
@@ -1069,19 +1125,12 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
                             break;
                         }
                     if (idx != 0xFFFFFFFFu) unit = ld_volatile_u32(&hq->unit[idx]) - 1u;  // (written before the slot was counted)
-                    ticket = 0xFFFFFFFFu;  // used
                     break;
                 }
-                if (!final_phase) break;   // not listed yet: keep the ticket for later
-                if (final_list) {          // never will be: the launch has no such sub-task
-                    ticket = 0xFFFFFFFFu;
-                    break;
-                }
+                if (final_list) break;  // the launch has no such sub-task
                 __nanosleep(1000);
             }
         }
-        ticket = __shfl_sync(FULL, ticket, 0);
-        *pending = ticket;
         idx = __shfl_sync(FULL, idx, 0);
         if (idx == 0xFFFFFFFFu) break;
         c = __shfl_sync(FULL, c, 0);
@@ -1104,38 +1153,9 @@ __device__ __noinline__ void finish_heavy_units(const RenderParams *gp, HeavyQue
         if (lane == 0) finished = atomicAdd(&hq->done[idx], 1u) + 1u;
         finished = __shfl_sync(FULL, finished, 0);
         if (finished != p.M) continue;
-        // last sub-task of the unit: continue the predecessor's sums with the M contributions, in copy order
+        // last sub-task of the unit: its sums can be finished as soon as the predecessor's are (finish_chain)
         __threadfence();
-        if (r.hit) {
-            float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
-            if (g > 0) {
-                const uint32_t want = frame_tag + g - 1u;  // (a deferred predecessor is further up the list: being worked on)
-                float4 sd, ss;
-                uint32_t spins = 0;
-                do {
-                    sd = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].d);
-                    ss = ld_relaxed_gpu(&state[(size_t)(g - 1u) * chain_stride + item].s);
-                    if (++spins > WAIT_SPINS) {
-                        watchdog_trip(watchdog, 3u);
-                        break;
-                    }
-                } while (__float_as_uint(sd.w) != want || __float_as_uint(ss.w) != want);
-                sum_d = f3(sd.x, sd.y, sd.z);
-                sum_s = f3(ss.x, ss.y, ss.z);
-            }
-            for (uint32_t k = 0; k < p.M; k++) {
-                const float4 a = ld_relaxed_gpu(slab + (size_t)k * 64u), b2 = ld_relaxed_gpu(slab + (size_t)k * 64u + 1);
-                sum_d = sum_d + f3(a.x, a.y, a.z);
-                sum_s = sum_s + f3(b2.x, b2.y, b2.z);
-            }
-            if (g + 1 != n_groups) {
-                const float tag = __uint_as_float(frame_tag + g);
-                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
-                st_relaxed_gpu(&state[(size_t)g * chain_stride + item].s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
-            } else {
-                store_direct_sample<POINTS>(p, r, sum_d, sum_s);
-            }
-        }
+        finish_chain<POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, idx, g, b);
     }
     if (COUNT && cn_out) {
         cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
@@ -1170,9 +1190,6 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
 // DEFER: with the deferral of very expensive units compiled in.  It costs a few per cent of steady-state
 // throughput (register pressure in the unit loop) and removes the tail of the launch, so the host selects
 // it when a launch has few units per warp -- a rank's share of a multi-GPU frame.
-#ifndef RT_HEAVY_HELP_EVERY
-#define RT_HEAVY_HELP_EVERY 8  // a warp looks for deferred sub-tasks every this many units (0: only at the end of the launch)
-#endif
 #ifndef RT_WAIT_BACKOFF_NS
 #define RT_WAIT_BACKOFF_NS 200  // sleep between two polls of a chained record that is not there yet (0: plain polling)
 #endif
@@ -1196,7 +1213,6 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
     Counters cn = {0, 0, 0, 0, 0, 0};
-    uint32_t units_done = 0, pending_ticket = 0xFFFFFFFFu;  // (DEFER: a sub-task ticket taken while helping, not ready yet)
 #ifdef RT_DBG_TAIL
     const uint32_t warp_id = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     unsigned long long dbg_t0 = dbg_globaltimer(), dbg_spin = 0, dbg_last_start = 0, dbg_worst = 0, dbg_worst_info = 0, dbg_cur_info = 0;
@@ -1204,19 +1220,6 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     uint32_t dbg_units = 0, dbg_helped = 0;
 #endif
     for (;;) {
-        if (RT_HEAVY_HELP_EVERY > 0 && DEFER && BEAM && deferring && (++units_done % (uint32_t)(RT_HEAVY_HELP_EVERY > 0 ? RT_HEAVY_HELP_EVERY : 1)) == 0u) {
-            // every 8th unit: are there deferred sub-tasks waiting?  Then do two of them now -- a deferred unit is worked
-            // off by many warps soon after it was listed instead of at the end of the launch, which is what is left of
-            // the tail of a small launch.  (One 8-byte load; the helper takes only tickets that are ready.)
-            unsigned int waiting = 0;
-            if (lane == 0) {
-                const unsigned long long v = *(const volatile unsigned long long *)&hq->next_task;  // (next_task, n_ready)
-                const unsigned int first_free = pending_ticket != 0xFFFFFFFFu ? pending_ticket : (unsigned int)(v & 0xFFFFFFFFull);
-                waiting = first_free / p.M < (unsigned int)(v >> 32);
-            }
-            if (__shfl_sync(FULL, waiting, 0))
-                finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, 0u, COUNT ? &cn : nullptr, watchdog, false, 2u, &pending_ticket);
-        }
         uint32_t unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
         unit = __shfl_sync(FULL, unit, 0);
@@ -1267,8 +1270,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         uint32_t cand[BEAM_MAX_CAND];  // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
         int n_cand = -1;
         int32_t last_occluder = -1;
-        bool defer = false;  // this lane wants the unit deferred
-        uint32_t inherited_slot = 0xFFFFFFFFu;  // ... because its predecessor is on the heavy list: the slot reserved for this unit
+        bool heavy = false;  // this lane's beam overflowed: M separate BVH walks, everybody else in the warp waiting
+        uint32_t inherited_slot = 0xFFFFFFFFu;  // the predecessor is on the heavy list: the slot that was reserved for this unit
         LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
         if (p.LM > 0) L = load_light(p, li0);
         if (r.hit) {
@@ -1290,7 +1293,6 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     const uint32_t td = __float_as_uint(sd.w), ts = __float_as_uint(ss.w);
                     if (td == want && ts == want) break;
                     if (DEFER && td == (want | CHAIN_DEFERRED)) {  // the predecessor is on the heavy list: so is this unit
-                        defer = true;
                         inherited_slot = __float_as_uint(sd.x) + 1u;
                         break;
                     }
@@ -1302,7 +1304,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 sum_s = f3(ss.x, ss.y, ss.z);
             }
             if (p.M > 1) cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, li0, p.K);
-            if (BEAM && !defer) {
+            if (BEAM) {
                 const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
                 // the same float operations as the copies' `lpos + rp * w2s`, which are monotonic in rp
                 const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
@@ -1311,19 +1313,19 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 const Beam beam = make_beam(r.P, lmin, lmax, pad);
                 const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
                 n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
-                if (DEFER) defer = n_cand == -1;  // overflow: M separate BVH walks, everybody else in the warp waiting
+                if (DEFER) heavy = n_cand == -1;
             }
-            if (DEFER && p.defer_all) defer = true;  // (tests)
+            if (DEFER && p.defer_all) heavy = true;  // (tests)
         }
         if (DEFER && BEAM && deferring) {
             __syncwarp();
-            const unsigned want_defer = __ballot_sync(FULL, defer);
-            if (want_defer) {
-                // A unit never waits for a deferred predecessor: either it inherits the slot that was reserved for it
-                // when the first unit of its chain was listed, or (fresh) it reserves slots for itself AND every later
-                // group of this batch at once -- all or nothing, so the list never holds a unit whose successors cannot
-                // follow it.  No room: processed in place (its predecessor is not on the list: nothing to wait for).
-                const unsigned inherit = __ballot_sync(FULL, inherited_slot != 0xFFFFFFFFu);
+            const unsigned heavy_lanes = __ballot_sync(FULL, heavy), inherit = __ballot_sync(FULL, inherited_slot != 0xFFFFFFFFu);
+            if (heavy_lanes | inherit) {
+                // A unit never waits for a listed predecessor: either it inherits the slot that was reserved for it when
+                // the first unit of its chain was listed, or (fresh: one of its beams overflowed) it reserves slots for
+                // itself AND every later group of this batch at once -- all or nothing, so the list never holds a unit
+                // whose successors cannot follow it.  No room: processed in place (its predecessor is then not on the
+                // list: nothing to wait for).
                 unsigned int idx = 0xFFFFFFFFu;
                 if (inherit) {
                     idx = __shfl_sync(FULL, inherited_slot, __ffs(inherit) - 1);
@@ -1343,12 +1345,43 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     }
                     idx = __shfl_sync(FULL, idx, 0);
                 }
-                if (idx != 0xFFFFFFFFu) {
+                if (idx != 0xFFFFFFFFu && heavy_lanes) {
+                    // very expensive: worked off as M sub-tasks by all warps once the unit queue is dry
                     defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (tag_base + group_index) | CHAIN_DEFERRED, !last && r.hit,
                                last && r.valid && !r.hit);
 #ifdef RT_DBG_TAIL
                     dbg_helped++;
 #endif
+                    continue;
+                }
+                if (idx != 0xFFFFFFFFu) {
+                    // Only its predecessor is listed, the unit itself is an ordinary one: its M contributions are computed
+                    // here and now, through the beams like any other unit's, and parked in the slot's scratch slab; what
+                    // waits for the predecessor is just the M ordered additions (finish_chain).  (Before: all M x 32 rays of
+                    // such a unit were traced again by BVH walks as sub-tasks -- most of the work of the final phase.)
+                    if (!last && r.hit) {  // successors must not wait for the record either
+                        const float tag = __uint_as_float((tag_base + group_index) | CHAIN_DEFERRED);
+                        st_relaxed_gpu(&own_rec->d, make_float4(__uint_as_float(idx), 0.0f, 0.0f, tag));
+                        st_relaxed_gpu(&own_rec->s, make_float4(0.0f, 0.0f, 0.0f, tag));
+                    }
+                    if (last && r.valid && !r.hit) p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (r.hit) {
+                        float4 *slab = hscratch + ((size_t)idx * p.M * 32u + lane) * 2u;  // + copy * 64
+                        if (COUNT && n_cand == BEAM_COVERED) cn.shadow += n_in_group;
+                        for (uint32_t l = 0; l < n_in_group; l++) {
+                            float3 dc = splat(0.0f), spc = splat(0.0f);
+                            if (n_cand != BEAM_COVERED)
+                                shade_pair<COUNT, 1>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, copy_position(p, L.pos, cloud, l), L.intensity, L.color, cull, cn, dc,
+                                                     spc, cand, n_cand, &last_occluder);
+                            st_relaxed_gpu(slab + (size_t)l * 64u, make_float4(dc.x, dc.y, dc.z, 0.0f));
+                            st_relaxed_gpu(slab + (size_t)l * 64u + 1, make_float4(spc.x, spc.y, spc.z, 0.0f));
+                        }
+                    }
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) atomicAdd(&hq->done[idx], p.M);  // all M contributions at once
+                    __threadfence();
+                    finish_chain<POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, idx, group_index, batch);
                     continue;
                 }
             }
@@ -1410,8 +1443,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog, true,
-                                          0u, &pending_ticket);
+        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif
