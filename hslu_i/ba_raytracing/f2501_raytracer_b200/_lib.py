@@ -65,7 +65,7 @@ class Config(C.Structure):
 
 class SceneInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint32), ("n_slots", C.c_uint32), ("bvh_depth", C.c_uint32), ("builder", C.c_uint32),
-                ("build_ms", C.c_double), ("upload_ms", C.c_double), ("device_bytes", C.c_uint64)]
+                ("build_ms", C.c_double), ("upload_ms", C.c_double), ("device_bytes", C.c_uint64), ("scratch_bytes", C.c_uint64)]
 
 
 class Stats(C.Structure):

@@ -59,7 +59,6 @@ struct rt_scene {
     uint64_t last_wave_points = 0;
     unsigned int *chain_done = nullptr;   // per batch of a window: tag of the window's last unit (slot reuse across windows)
     size_t chain_done_cap = 0;
-    size_t info_scratch_bytes = 0;        // chained-record scratch of the last direct-lighting frame
     unsigned int *pass_counters = nullptr;  // work counter of direct_kernel
     HeavyQueue *heavy_queue = nullptr;      // list of deferred (very expensive) units of direct_kernel
     RenderParams *d_params = nullptr;       // global-memory copy of the kernel parameters for direct_kernel's out-of-line paths
@@ -358,7 +357,6 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         s->frame_serial += (uint32_t)tags;
         pd.chain_window = chain_window;
         pd.chain_done = s->chain_done;
-        s->info_scratch_bytes = s->direct_cap + s->chain_done_cap;
         using kernel_t = void (*)(const RenderParams, uint32_t, uint32_t, unsigned int *, DirectState *, HeavyQueue *, float4 *, const RenderParams *,
                                   unsigned int *);
         kernel_t kernel;
@@ -968,6 +966,8 @@ const char *rt_last_kernel(const rt_scene *s) { return s ? s->last_kernel : ""; 
 int rt_scene_get_info(const rt_scene *s, rt_scene_info *out) {
     if (!s || !out) return rt_fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_get_info: null argument");
     *out = s->info;
+    out->scratch_bytes = s->samples_cap + s->primary_cap + s->direct_cap + s->chain_done_cap + s->wave_points_cap + s->wave_contrib_cap + s->wave_heads_cap +
+                         s->heavy_scratch_cap + (s->heavy_queue ? sizeof(HeavyQueue) : 0) + s->clouds_cap + s->clouds_raw_cap + s->slab_cap;
     return RT_OK;
 }
 

@@ -179,6 +179,8 @@ typedef struct rt_scene_info {
     double build_ms;         /* BVH build + flattening */
     double upload_ms;        /* host-to-device copies (0 for the device builder: built in place) */
     uint64_t device_bytes;   /* nodes + slots + normals + materials + lights */
+    uint64_t scratch_bytes;  /* per-scene render scratch currently allocated: samples, primary hits, chained records
+                                (bounded window), path queue of the bounce configs, deferral scratch */
 } rt_scene_info;
 int rt_scene_get_info(const rt_scene *scene, rt_scene_info *out);
 

@@ -579,6 +579,14 @@ def test_asynchronous_frames_are_checked(pkg, scenes):
     assert dev.dominant_kernel_name().startswith("direct_kernel<false,true,")
     info = dev.bvh_info()
     assert info["n_nodes"] > 1000 and info["n_slots"] >= flat.n_primitives and info["build_ms"] > 0
+    # the chained records are bounded: the full headline frame (245 760 batches x 4 generations = 1 GB in round 1)
+    # leaves well under 400 MB of scratch in total (samples 126 MB + primary hits 126 MB + record window 128 MB)
+    fresh = pkg.DeviceScene(flat)
+    try:
+        fresh.render(pkg.RenderConfig.from_features(feat, 4))
+        assert 0 < fresh.bvh_info()["scratch_bytes"] < 420e6
+    finally:
+        fresh.close()
 
 
 def test_place_tiles_and_kernel_times(pkg, scenes):
