@@ -390,6 +390,7 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
             hq = s->heavy_queue;
             if ((rc = upload_params(s, pd, stream))) return rc;
         }
+        if (beams && !defer && (rc = upload_params(s, pd, stream))) return rc;  // (the out-of-line paths read the parameters from global memory)
         unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
         if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
         if (record_events)
@@ -397,7 +398,7 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         snprintf(s->last_kernel, sizeof(s->last_kernel), points ? "paths_kernel + direct_kernel<%s,%s,%s,points> + gather_paths_kernel" : "direct_kernel<%s,%s,%s>",
                  count ? "true" : "false", beams ? "true" : "false", defer ? "true" : "false");
         s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, beams ? s->d_params : nullptr,
                                                   s->d_watchdog);
         CU_CHECK(cudaGetLastError());
         if (record_events) {
