@@ -390,7 +390,6 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
             hq = s->heavy_queue;
             if ((rc = upload_params(s, pd, stream))) return rc;
         }
-        if (beams && !defer && (rc = upload_params(s, pd, stream))) return rc;  // (the out-of-line paths read the parameters from global memory)
         unsigned int *unit_counter = hq ? &hq->unit_counter : s->pass_counters;
         if (!hq) CU_CHECK(cudaMemsetAsync(s->pass_counters, 0, sizeof(unsigned int), stream));
         if (record_events)
@@ -398,7 +397,7 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         snprintf(s->last_kernel, sizeof(s->last_kernel), points ? "paths_kernel + direct_kernel<%s,%s,%s,points> + gather_paths_kernel" : "direct_kernel<%s,%s,%s>",
                  count ? "true" : "false", beams ? "true" : "false", defer ? "true" : "false");
         s->frame_has_watchdog = true;  // every variant has bounded wait loops (chained records)
-        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, beams ? s->d_params : nullptr,
+        kernel<<<dgrid, CTA_THREADS, 0, stream>>>(pd, passes, frame_tag, unit_counter, s->direct_state, hq, s->heavy_scratch, s->d_params,
                                                   s->d_watchdog);
         CU_CHECK(cudaGetLastError());
         if (record_events) {
@@ -1562,31 +1561,36 @@ int rt_multi_render(rt_multi *m, const rt_config *cfg, uint32_t *out_argb, uint8
         }
     if (any_peer) CU_CHECK(cudaMemcpyAsync(m->frame_host, m->frame, n_pix * sizeof(uint32_t), cudaMemcpyDeviceToHost, m->stream0));
     CU_CHECK(cudaStreamSynchronize(m->stream0));
-    for (uint32_t r = 0; r < n; r++) {
-        CU_CHECK(cudaSetDevice(m->devices[r]));
-        CU_CHECK(cudaEventSynchronize(m->done[r]));
-        if ((rc = check_watchdog(m->scenes[r], true))) return rc;
-    }
-    // ImageBuffer semantics: only hit pixels are stored (pixel != 0 <=> hit, see rt_render)
+    // every worker: its device's frames are valid (watchdog), then its rows go into the caller's buffer -- the merge
+    // (ImageBuffer semantics: only hit pixels are stored; pixel != 0 <=> hit, see rt_render) runs on all workers at once
     const bool zero_misses = (cfg->flags & RT_FLAG_ZERO_MISSES) != 0;
-    auto merge_row = [&](const uint32_t *src, size_t row) {
-        uint32_t *dst = out_argb + row * W;
-        if (zero_misses)
-            memcpy(dst, src, (size_t)W * sizeof(uint32_t));
-        else
-            for (uint32_t x = 0; x < W; x++) dst[x] = src[x] ? src[x] : dst[x];
-        if (out_hit_mask) {
-            uint8_t *dm = out_hit_mask + row * W;
-            for (uint32_t x = 0; x < W; x++) dm[x] = src[x] != 0u;
-        }
-    };
-    for (uint32_t r = 0; r < n; r++) {
-        const uint32_t rows = local_rows_of(&cfgs[r]);
-        for (uint32_t lr = 0; lr < rows; lr++) {
-            const size_t row = image_row_of(&cfgs[r], lr);
-            merge_row(m->peer[r] ? m->frame_host + row * W : m->slab_host[r] + (size_t)lr * W, row);
-        }
-    }
+    m->pool->run([&](int r) {
+        auto body = [&]() -> int {
+            CU_CHECK(cudaSetDevice(m->devices[r]));
+            CU_CHECK(cudaEventSynchronize(m->done[r]));
+            int rc2 = check_watchdog(m->scenes[r], true);
+            if (rc2) return rc2;
+            const uint32_t rows = local_rows_of(&cfgs[r]);
+            for (uint32_t lr = 0; lr < rows; lr++) {
+                const size_t row = image_row_of(&cfgs[r], lr);
+                const uint32_t *src = m->peer[r] ? m->frame_host + row * W : m->slab_host[r] + (size_t)lr * W;
+                uint32_t *dst = out_argb + row * W;
+                if (zero_misses)
+                    memcpy(dst, src, (size_t)W * sizeof(uint32_t));
+                else
+                    for (uint32_t x = 0; x < W; x++) dst[x] = src[x] ? src[x] : dst[x];
+                if (out_hit_mask) {
+                    uint8_t *dm = out_hit_mask + row * W;
+                    for (uint32_t x = 0; x < W; x++) dm[x] = src[x] != 0u;
+                }
+            }
+            return RT_OK;
+        };
+        rcs[r] = body();
+        if (rcs[r]) errs[r] = rt_last_error();
+    });
+    for (uint32_t r = 0; r < n; r++)
+        if (rcs[r]) return rt_fail(rcs[r], "rt_multi_render: device %u: %s", r, errs[r].c_str());
     if (stats) {
         memset(stats, 0, sizeof(*stats));
         for (uint32_t r = 0; r < n; r++) {

@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
             p.samples[sample_index] = make_float4(acc.x, acc.y, acc.z, sample_valid ? 1.0f : 0.0f);
             have_item = false;
         }
+        bool exhausted = false;  // the fetch of this round found the queue empty
         {
             bool need = !have_ray;
             uint32_t need_mask = __ballot_sync(FULL, need);
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
                 }
                 base = __shfl_sync(FULL, base, leader);
                 grant = __shfl_sync(FULL, grant, leader);
+                exhausted = base >= p.n_items;
                 const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
                 const uint32_t item = base + rank;
                 const ItemInfo it = decode_item(p, item);
@@ -381,7 +383,10 @@ __global__ void __launch_bounds__(CTA_THREADS, RT_MIN_CTAS_PER_SM) render_kernel
                 }
             }
         }
-        if (!__any_sync(FULL, have_ray)) break;
+        if (!__any_sync(FULL, have_ray)) {  // (a round of nothing but padding items must not end the warp: see paths_kernel)
+            if (exhausted) break;
+            continue;
+        }
 
         // ---------------------------------------------------------------- closest hit (per lane)
         float3 d = splat(0.0f), P = splat(0.0f), N = splat(0.0f);
@@ -638,6 +643,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) paths_kernel(const RenderParam
             pq.sample_head[sample_slot] = last_point;
             have_item = false;
         }
+        bool exhausted = false;  // the fetch of this round found the queue empty
         {
             const bool need = !have_ray;
             const uint32_t need_mask = __ballot_sync(FULL, need);
@@ -652,6 +658,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) paths_kernel(const RenderParam
                 }
                 base = __shfl_sync(FULL, base, leader);
                 grant = __shfl_sync(FULL, grant, leader);
+                exhausted = base >= pq.n_chunk_items;
                 const uint32_t rank = __popc(need_mask & ((1u << lane) - 1u));
                 const uint32_t in_chunk = base + rank;
                 const uint32_t item = pq.first_item + in_chunk;
@@ -677,7 +684,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 4) paths_kernel(const RenderParam
                 }
             }
         }
-        if (!__any_sync(FULL, have_ray)) break;
+        if (!__any_sync(FULL, have_ray)) {
+            // Nobody got a ray.  That ends the warp only when the queue is empty: a round may hand out nothing but
+            // padding items (the lower half of the last tile row when the height is not a multiple of 4), and a warp
+            // that left then would leave the items behind it to the others -- at 1140x950 every warp of the grid
+            // left that way before the row was finished (round-2 finding: stale list heads in the last two rows).
+            if (exhausted) break;
+            continue;
+        }
 
         // ---------------------------------------------------------------- closest hit (per lane)
         float3 d = splat(0.0f), P = splat(0.0f), N = splat(0.0f);
@@ -1083,49 +1097,6 @@ __device__ __noinline__ void finish_chain(const RenderParams *gp, HeavyQueue *hq
     }
 }
 
-// The M shadow queries of every lane in `mask` (lanes whose beam overflowed: one BVH walk per copy), done by the whole
-// warp: one such lane at a time, its sample broadcast, copy c traced and shaded by lane c, the contributions handed back
-// and added by the owner in copy order -- the sums the owner's own loop would have formed.  Out of line, parameters from
-// their global-memory copy (register budget of the caller).
-template <bool COUNT>
-__device__ __noinline__ void coop_overflow_lanes(const RenderParams *gp, unsigned mask, float3 P, float3 N, float3 d, float3 mcolor, float mshininess,
-                                                 uint32_t cloud, uint32_t li, float3 &sum_d, float3 &sum_s, Counters *cn_out) {
-    const RenderParams &p = *gp;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const bool cull = (p.flags & RT_FLAG_BACKFACE_CULLING) != 0;
-    const LightCopy L = load_light(p, li);
-    Counters cn = {0, 0, 0, 0, 0, 0};
-    while (mask) {
-        const int o = __ffs(mask) - 1;
-        mask &= mask - 1u;
-        const float3 oP = f3(__shfl_sync(FULL, P.x, o), __shfl_sync(FULL, P.y, o), __shfl_sync(FULL, P.z, o));
-        const float3 oN = f3(__shfl_sync(FULL, N.x, o), __shfl_sync(FULL, N.y, o), __shfl_sync(FULL, N.z, o));
-        const float3 od = f3(__shfl_sync(FULL, d.x, o), __shfl_sync(FULL, d.y, o), __shfl_sync(FULL, d.z, o));
-        const float3 oc = f3(__shfl_sync(FULL, mcolor.x, o), __shfl_sync(FULL, mcolor.y, o), __shfl_sync(FULL, mcolor.z, o));
-        const float os = __shfl_sync(FULL, mshininess, o);
-        const uint32_t ocloud = __shfl_sync(FULL, cloud, o);
-        for (uint32_t base = 0; base < p.M; base += 32u) {
-            const uint32_t c = base + lane;
-            float3 dc = splat(0.0f), spc = splat(0.0f);
-            if (c < p.M) shade_pair<COUNT, 2>(p, oP, oN, od, oc, os, copy_position(p, L.pos, ocloud, c), L.intensity, L.color, cull, cn, dc, spc);
-            const uint32_t n = min(32u, p.M - base);
-            for (uint32_t j = 0; j < n; j++) {  // copy order: the owner's running sums are the reference's
-                const float3 a = f3(__shfl_sync(FULL, dc.x, j), __shfl_sync(FULL, dc.y, j), __shfl_sync(FULL, dc.z, j));
-                const float3 b = f3(__shfl_sync(FULL, spc.x, j), __shfl_sync(FULL, spc.y, j), __shfl_sync(FULL, spc.z, j));
-                if ((int)lane == o) {
-                    sum_d = sum_d + a;
-                    sum_s = sum_s + b;
-                }
-            }
-        }
-    }
-    if (COUNT && cn_out) {
-        cn_out->closest += cn.closest; cn_out->shadow += cn.shadow; cn_out->box += cn.box;
-        cn_out->tri += cn.tri; cn_out->sph += cn.sph; cn_out->beam_prim += cn.beam_prim;
-    }
-}
-
 // Phase B of direct_kernel (see above).  Out of line, parameters read from their global-memory copy, so
 // that it does not weigh on the register allocation of the unit loop.
 template <bool COUNT, bool POINTS>
@@ -1440,20 +1411,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         // every lane shades its own sample against the group's light copies, in order (a beam that one opaque
         // triangle occludes entirely is M occluded queries: nothing to trace, nothing to add)
         if (COUNT && r.hit && n_cand == BEAM_COVERED) cn.shadow += n_in_group;
-        // Lanes whose beam overflowed its candidate list have to walk the BVH once per copy.  Left to themselves they do
-        // their M walks one after the other while the rest of the warp has long finished (14 of 32 lanes active on the
-        // 4 M-triangle scene; the 1-2 ms units of the headline frame).  When they are few, the WARP does them instead:
-        // one overflowing lane at a time, its M copies spread over the lanes (coop_overflow_lanes) -- k rounds of one
-        // walk instead of M walks at k lanes.
-        bool own_walks = true;
-        if (BEAM && gp != nullptr) {
-            const unsigned overflow = __ballot_sync(FULL, r.hit && n_cand == -1);
-            if (overflow && 4u * (uint32_t)__popc(overflow) <= 3u * p.M) {
-                coop_overflow_lanes<COUNT>(gp, overflow, r.P, r.N, r.d, r.mcolor, r.mshininess, cloud, li0, sum_d, sum_s, COUNT ? &cn : nullptr);
-                own_walks = false;
-            }
-        }
-        if (r.hit && n_cand != BEAM_COVERED && (own_walks || n_cand != -1)) {
+        if (r.hit && n_cand != BEAM_COVERED) {
             for (uint32_t l = 0; l < n_in_group; l++) {
                 float3 dc, spc;
                 if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights

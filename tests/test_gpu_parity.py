@@ -671,6 +671,32 @@ def test_wavefront_equals_the_megakernel(pkg, scenes, monkeypatch, scene_name, f
     assert np.array_equal(small.buffer, mega.buffer) and np.array_equal(small.hit_mask, mega.hit_mask)
 
 
+def test_ragged_last_tile_row_of_a_bounce_frame(pkg, oracle_mod, scenes, monkeypatch):
+    """1140x950 with 16 samples per pixel: 950 is not a multiple of the 4-row work tiles, so the lower half of the last
+    tile row is padding -- runs of 256 padding items between the real ones.  A warp of the path walk that was handed
+    nothing but padding used to leave for good; near the end of the queue (small grants) every warp of the grid left
+    that way before the row was finished, and the last two image rows kept stale data (found in round 2 by comparing
+    rt_multi_render with rt_render: 600 pixels, run-to-run differences).  The bottom rows against the oracle, both
+    forms of the bounce path against each other on the whole frame, and twice in a row."""
+    feat = "realistic,anti_aliasing,simd_render,medium_resolution"
+    flat, dev = scenes("main", feat)
+    rc = pkg.RenderConfig.from_features(feat, 0)
+    W, H = rc.cfg.width, rc.cfg.height
+    assert (W, H, rc.samples_per_pixel) == (1140, 950, 16) and H % 4 == 2
+    a, _ = dev.render(rc)
+    b, _ = dev.render(rc)
+    assert np.array_equal(a.buffer, b.buffer) and np.array_equal(a.hit_mask, b.hit_mask)
+    monkeypatch.setenv("RT_WAVEFRONT", "0")
+    mega, _ = dev.render(rc)
+    assert np.array_equal(a.buffer, mega.buffer) and np.array_equal(a.hit_mask, mega.hit_mask)
+    ys, xs = np.mgrid[H - 12:H, 0:W]
+    pix = (ys * W + xs).astype(np.uint32).ravel()
+    o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+    assert o_mask[pix].mean() > 0.5
+    assert_image_parity(a, o_argb, o_mask, pix)
+    assert_image_parity(mega, o_argb, o_mask, pix)
+
+
 def test_gpu_frame_vs_reference_render_dense_grid(pkg, scenes):
     """The CUDA path against the reference's OWN committed render (output.png, crate defaults + simd_render):
     1748 pixels on a 25-px grid (tests/golden/output_png_kats.json).  Hit mask identical; colours equal up to
