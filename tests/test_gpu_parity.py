@@ -692,7 +692,7 @@ def test_ragged_last_tile_row_of_a_bounce_frame(pkg, oracle_mod, scenes, monkeyp
     ys, xs = np.mgrid[H - 12:H, 0:W]
     pix = (ys * W + xs).astype(np.uint32).ravel()
     o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
-    assert o_mask[pix].mean() > 0.5
+    assert o_mask[pix].mean() > 0.2  # (the bottom rows are partly border)
     assert_image_parity(a, o_argb, o_mask, pix)
     assert_image_parity(mega, o_argb, o_mask, pix)
 
