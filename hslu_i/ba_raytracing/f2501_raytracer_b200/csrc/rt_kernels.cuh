@@ -28,6 +28,9 @@ namespace rtd {
 #define RT_EMPTY_LIST_SKIP 1  // a beam without candidates: no list walk (see RT_SELF_CULL in rt_device.cuh)
 #endif
 #ifndef RT_CTA_THREADS
+#ifndef RT_FACING_FIRST
+#define RT_FACING_FIRST 1  // no shadow query towards a light the surface faces away from, no beam towards a light box entirely behind it
+#endif
 #define RT_CTA_THREADS 128
 #endif
 #ifndef RT_MIN_CTAS_PER_SM
@@ -172,6 +175,13 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const bool d2_ok = (d2 > 1e-30f) & (d2 < 1e30f);  // inside the range of the sequences above (false for NaN)
     float3 ldir = l2p * rcp_rn_normal(sqrt_rn_normal(d2));
     if (!d2_ok) ldir = normalized3(l2p);
+    // `light_valid` (raytracer_renderer.rs:849): a light the surface does not face adds exactly nothing, whatever its
+    // shadow query answers -- so the query is not made (RT_FACING_FIRST; the reference casts the ray and drops the result).
+    const float diffuse = smax(dot3(hn, ldir), 0.0f);
+    if (RT_FACING_FIRST && !(diffuse > 0.0f)) {
+        if (COUNT) cn.shadow++;
+        return;
+    }
     ShadowResult sh;
     sh.occluded = false;
     sh.opacity = 1.0f;
@@ -205,7 +215,6 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     }
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
-    const float diffuse = smax(dot3(hn, ldir), 0.0f);
     if (sh.occluded || !(diffuse > 0.0f)) return;
     const float ldist = sqrt_fast(dot3(l2p, l2p)) + EPS;  // from here on: colour only (fast math, rt_device.cuh)
     const float cosn = dot3(l2p, hn);                       // cosi = cosn / ldist > 0 <=> cosn > 0 (ldist > 0)
@@ -274,9 +283,12 @@ __device__ __noinline__ LightSums beam_lighting(const RenderParams *gp, float3 P
         const LightCopy L = load_light(p, li);
         const uint32_t cloud = cloud_index(p.seed, cloud_x, pix_y, li, p.K);
         const float3 lmin = L.pos + clo, lmax = L.pos + chi;  // the copies' `lpos + rp * w2s` is monotonic in rp
-        const Beam beam = make_beam(P, lmin, lmax, pad);
         const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
-        const int n_cand = beam_collect<COUNT>(sc, beam, P, C - P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+        int n_cand = BEAM_COVERED;  // (a light box behind the surface is treated like a covered beam: nothing to add)
+        if (!(RT_FACING_FIRST && light_box_behind(N, C - P, hh))) {
+            const Beam beam = make_beam(P, lmin, lmax, pad);
+            n_cand = beam_collect<COUNT>(sc, beam, P, C - P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+        }
         if (n_cand == BEAM_COVERED) {  // one opaque triangle occludes all M copies: M occluded queries, nothing to add
             if (COUNT) cn.shadow += p.M;
             continue;
@@ -1324,9 +1336,13 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 const float3 lmin = L.pos + f3(p.cloud_lo[0], p.cloud_lo[1], p.cloud_lo[2]) * w2s;
                 const float3 lmax = L.pos + f3(p.cloud_hi[0], p.cloud_hi[1], p.cloud_hi[2]) * w2s;
                 const float pad = fmaf(0.25f, sc.box_pad, 2.0f * p.eps_d);
-                const Beam beam = make_beam(r.P, lmin, lmax, pad);
                 const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));
-                n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+                if (RT_FACING_FIRST && light_box_behind(r.N, C - r.P, hh)) {
+                    n_cand = BEAM_COVERED;  // like a covered beam: M queries nobody needs, nothing to add (rt_device.cuh)
+                } else {
+                    const Beam beam = make_beam(r.P, lmin, lmax, pad);
+                    n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
+                }
                 if (DEFER) heavy = n_cand == -1;
             }
             if (DEFER && p.defer_all) heavy = true;  // (tests)

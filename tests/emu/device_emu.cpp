@@ -144,4 +144,28 @@ int emu_beam_shadows(void *h, uint32_t flags, const float *P3, const float *lmin
     return n_cand;
 }
 
+// light_box_behind (rt_device.cuh) against the per-copy test of shade_pair (rt_kernels.cuh): for n cases (P, N, box),
+// out_behind[i] = the box test; out_facing[i] = how many of the case's m copies pass `dot3(N, normalize(x - P)) > 0`,
+// evaluated with shade_pair's own operations.  The product relies on: behind => no copy faces.
+void emu_light_box_behind(const float *P3, const float *N3, const float *lmin3, const float *lmax3, const float *copies, uint32_t n, uint32_t m,
+                          int *out_behind, int *out_facing) {
+    for (uint32_t i = 0; i < n; i++) {
+        const float3 P = f3(P3[3 * i], P3[3 * i + 1], P3[3 * i + 2]), N = f3(N3[3 * i], N3[3 * i + 1], N3[3 * i + 2]);
+        const float3 lmin = f3(lmin3[3 * i], lmin3[3 * i + 1], lmin3[3 * i + 2]), lmax = f3(lmax3[3 * i], lmax3[3 * i + 1], lmax3[3 * i + 2]);
+        const float3 C = (lmin + lmax) * 0.5f, hh = (lmax - lmin) * 0.5f + splat(1e-6f * (fabsf(C.x) + fabsf(C.y) + fabsf(C.z)));  // (as direct_kernel)
+        out_behind[i] = light_box_behind(N, C - P, hh) ? 1 : 0;
+        int facing = 0;
+        for (uint32_t c = 0; c < m; c++) {
+            const float *x = copies + 3 * ((size_t)i * m + c);
+            const float3 l2p = f3(x[0], x[1], x[2]) - P;
+            const float d2 = dot3(l2p, l2p);
+            const bool d2_ok = (d2 > 1e-30f) & (d2 < 1e30f);
+            float3 ldir = l2p * rcp_rn_normal(sqrt_rn_normal(d2));
+            if (!d2_ok) ldir = normalized3(l2p);
+            if (smax(dot3(N, ldir), 0.0f) > 0.0f) facing++;
+        }
+        out_facing[i] = facing;
+    }
+}
+
 }  // extern "C"

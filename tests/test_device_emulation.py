@@ -36,6 +36,7 @@ def _build_emu(lib_name, defines=()):
     lib.emu_scene_destroy.argtypes = [vp]
     lib.emu_trace_closest.argtypes = [vp, u32, vp, u32, vp, vp]
     lib.emu_trace_shadow.argtypes = [vp, u32, vp, vp, u32, vp]
+    lib.emu_light_box_behind.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp, vp]
     lib.emu_beam_shadows.restype = C.c_int
     lib.emu_beam_shadows.argtypes = [vp, u32, vp, vp, vp, f32, vp, u32, vp, vp, vp]
     return lib
@@ -262,3 +263,39 @@ def test_beam_degenerate_inputs_equal_per_ray_traversal(pkg, emu):
             assert np.array_equal(out_list[free].view(np.uint32), out_ray[free].view(np.uint32))
     finally:
         emu.emu_scene_destroy(h)
+
+
+def test_a_light_box_behind_the_surface_has_no_facing_copy(emu):
+    """RT_FACING_FIRST (rt_kernels.cuh): direct_kernel builds no beam towards a light whose box of copies is entirely
+    behind the surface (light_box_behind, rt_device.cuh), relying on every copy then failing shade_pair's own
+    N.L > 0 test.  Random and adversarial cases -- grazing boxes, boxes touching the tangent plane, corner copies,
+    huge and tiny scales, NaN normals -- with the per-copy test evaluated by shade_pair's operations."""
+    rng = np.random.default_rng(5)
+    n, m = 200000, 12
+    P = rng.uniform(-1, 1, (n, 3)).astype(F)
+    N = rng.normal(size=(n, 3)).astype(F)
+    N /= np.linalg.norm(N, axis=1, keepdims=True).astype(F)
+    N[::17] *= F(0.37)  # (interpolated shading normals are not unit length)
+    centre = P + rng.normal(size=(n, 3)).astype(F) * rng.choice([1e-3, 0.05, 1.0, 30.0], (n, 1)).astype(F)
+    half = np.abs(rng.normal(size=(n, 3))).astype(F) * rng.choice([0.0, 1e-4, 0.02, 0.5], (n, 1)).astype(F)
+    # a third of the cases: the box pushed so that its most-facing corner lies (almost) in the tangent plane
+    k = n // 3
+    reach = np.sum(np.abs(N[:k]) * half[:k], axis=1) + np.sum(N[:k] * (centre[:k] - P[:k]), axis=1)
+    nn = np.sum(N[:k] * N[:k], axis=1)
+    centre[:k] -= (N[:k] * (reach / nn)[:, None] * rng.choice([0.999, 1.0, 1.0001, 1.001, 1.5], (k, 1))).astype(F)
+    scale = rng.choice([1e-3, 1.0, 1e3], (n, 1)).astype(F)
+    P, centre, half = (P * scale).astype(F), (centre * scale).astype(F), (half * scale).astype(F)
+    lmin, lmax = (centre - half).astype(F), (centre + half).astype(F)
+    u = rng.random((n, m, 3)).astype(F)
+    u[:, :8] = np.array([[(i >> 0) & 1, (i >> 1) & 1, (i >> 2) & 1] for i in range(8)], F)  # the corners first
+    copies = np.ascontiguousarray(np.clip(lmin[:, None, :] + u * (lmax - lmin)[:, None, :], lmin[:, None, :], lmax[:, None, :]).astype(F))
+    N[5] = np.nan
+    P[6, 1] = np.nan
+    behind, facing = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    P, N, lmin, lmax = (np.ascontiguousarray(a, F) for a in (P, N, lmin, lmax))
+    emu.emu_light_box_behind(ptr(P), ptr(N), ptr(lmin), ptr(lmax), ptr(copies), n, m, ptr(behind), ptr(facing))
+    assert behind[5] == 0 and behind[6] == 0
+    assert not np.any((behind == 1) & (facing > 0))
+    assert behind.mean() > 0.2 and (facing == 0).mean() < 0.7  # both outcomes are exercised
+    # the test is not vacuous where it matters: most boxes without a facing copy are recognised
+    assert ((behind == 1) & (facing == 0)).sum() > 0.8 * (facing == 0).sum()
