@@ -305,8 +305,8 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
     int rc = RT_OK;
     {
         // direct lighting only: one pass per light group over all samples
-        const uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);
-        const uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
+        uint32_t n_groups = p.M > 1 ? s->d.n_lights : (p.LM ? 1u : 0u);  // (soft shadows: per light; regrouped below)
+        uint32_t passes = std::max(n_groups, 1u);  // a scene without lights still writes its samples
         if (passes > MAX_PASSES) return rt_fail(RT_ERR_INVALID_ARGUMENT, "too many lights for the soft-shadow path (%u > %u)", passes, MAX_PASSES);
         if ((uint64_t)warps_needed * passes >= (1ull << 32))
             return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call: %llu work units (limit 2^32); render it in row tiles",
@@ -326,6 +326,18 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         uint32_t defer_below = 100;
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
+        // Soft shadows: how many lights a unit takes in a row.  The deferring variant works per light (its units are
+        // small on purpose); everywhere else a unit lights its 32 samples with ALL lights, the running sums staying in
+        // registers -- no chained records, no waits, a fifth of the unit bookkeeping (measured: profiles/README.md).
+        // RT_LIGHTS_PER_UNIT (A/B runs, tests) selects anything in between; groups of lights are then chained as before.
+        uint32_t lights_per_unit = 1;
+        if (pd.M > 1 && !defer && n_groups > 0) {
+            lights_per_unit = n_groups;
+            if (const char *e = getenv("RT_LIGHTS_PER_UNIT")) lights_per_unit = (uint32_t)std::max(1, std::min<int>(atoi(e), (int)n_groups));
+            n_groups = (n_groups + lights_per_unit - 1) / lights_per_unit;
+            passes = n_groups;
+        }
+        pd.lights_per_unit = lights_per_unit;
         // Chained records between the light groups of a batch (direct_kernel): windows of `chain_window` batches with
         // two generations each; the DEFER variant keeps one window with every generation.
         // The window must be several times the number of resident warps: a unit's predecessor was handed out one window
@@ -340,7 +352,8 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;
         {
             const size_t before = s->direct_cap, before_done = s->chain_done_cap;
-            rc = grow(s->direct_state, s->direct_cap, std::max<size_t>((size_t)chain_window * 32 * gens, 1) * sizeof(DirectState));
+            const size_t n_records = passes > 1 ? (size_t)chain_window * 32 * gens : 1;  // (one group: nothing is chained)
+            rc = grow(s->direct_state, s->direct_cap, n_records * sizeof(DirectState));
             if (rc) return rc;
             if ((rc = grow(s->chain_done, s->chain_done_cap, (size_t)chain_window * sizeof(unsigned int)))) return rc;
             if (s->direct_cap != before) CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));  // no stale tags

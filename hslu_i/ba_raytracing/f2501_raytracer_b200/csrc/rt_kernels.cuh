@@ -82,6 +82,7 @@ struct RenderParams {
     uint32_t heavy_cap;    // direct_kernel: deferred units per launch (<= HEAVY_CAP; beyond: processed in place)
     uint32_t defer_all;    // tests only (RT_DEFER_ALL): every unit asks for deferral
     uint32_t chain_window; // direct_kernel: batches per window of the chained records (see direct_kernel)
+    uint32_t lights_per_unit;  // direct_kernel (soft shadows, not DEFER): lights a unit takes in a row (>= 1)
     unsigned int *chain_done;  // per batch of a window: tag of the window's last unit of that batch (slot reuse)
     PathQueue pq;          // bounce configs: the shading points of the chunk being rendered
     float4 *samples;               // local_rows * width * S : (r, g, b, valid)
@@ -1235,6 +1236,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
     const uint32_t window = DEFER ? n_batches : p.chain_window;  // batches per window (>= 1)
+    const uint32_t lpu = (!DEFER && p.M > 1) ? p.lights_per_unit : 1u;  // lights per unit (soft shadows); DEFER: a unit is one light
     const uint32_t window_units = window * n_groups;
     const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
@@ -1290,16 +1292,10 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         if (COUNT && !POINTS && r.valid && group_index == 0) cn.closest++;  // (POINTS: counted where the ray was traced)
         // lanes of a batch that missed sit the batch out but stay with the warp
         float3 sum_d = splat(0.0f), sum_s = splat(0.0f);
-        const uint32_t li0 = p.M > 1 ? group_index : 0u;
         const uint32_t n_in_group = p.M > 1 ? p.M : p.LM;
-        uint32_t cloud = 0u;
         uint32_t cand[BEAM_MAX_CAND];  // shadow beam: one BVH walk for the M copies of this light (rt_device.cuh)
-        int n_cand = -1;
-        int32_t last_occluder = -1;
-        bool heavy = false;  // this lane's beam overflowed: M separate BVH walks, everybody else in the warp waiting
         uint32_t inherited_slot = 0xFFFFFFFFu;  // the predecessor is on the heavy list: the slot that was reserved for this unit
-        LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
-        if (p.LM > 0) L = load_light(p, li0);
+        bool unit_parked = false;               // (DEFER) the unit went to the heavy list or parked its contributions: nothing to store here
         if (r.hit) {
             if (group_index > 0) {
                 // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
@@ -1329,6 +1325,19 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 sum_d = f3(sd.x, sd.y, sd.z);
                 sum_s = f3(ss.x, ss.y, ss.z);
             }
+        }
+        // the unit's lights, in the reference's order (soft shadows: `lpu` lights of M copies each; hard shadows: one
+        // group of all lights).  The running sums stay in registers from one light to the next.
+        for (uint32_t gl = 0; gl < lpu; gl++) {
+        const uint32_t li0 = p.M > 1 ? group_index * lpu + gl : 0u;
+        if (gl > 0 && li0 >= sc.n_lights) break;
+        uint32_t cloud = 0u;
+        int n_cand = -1;
+        int32_t last_occluder = -1;
+        bool heavy = false;  // this lane's beam overflowed: M separate BVH walks, everybody else in the warp waiting
+        LightCopy L = {splat(0.0f), splat(0.0f), 0.0f};
+        if (p.LM > 0) L = load_light(p, li0);
+        if (r.hit) {
             if (p.M > 1) cloud = cloud_index(p.seed, packet_noaa ? r.pix_x / 8u : r.pix_x, r.pix_y, li0, p.K);
             if (BEAM) {
                 const float3 w2s = f3(p.w2s_w, p.w2s_h, p.w2s_d);
@@ -1382,7 +1391,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
                     dbg_helped++;
 #endif
-                    continue;
+                    unit_parked = true;
+                    break;
                 }
                 if (idx != 0xFFFFFFFFu) {
                     // Only its predecessor is listed, the unit itself is an ordinary one: its M contributions are computed
@@ -1412,7 +1422,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     if (lane == 0) atomicAdd(&hq->done[idx], p.M);  // all M contributions at once
                     __threadfence();
                     finish_chain<POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, idx, group_index, batch);
-                    continue;
+                    unit_parked = true;
+                    break;
                 }
             }
         }
@@ -1450,6 +1461,8 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             }
         }
 #endif
+        }  // lights of the unit
+        if (DEFER && unit_parked) continue;
         if (r.hit) {
             if (!last) {
                 const float tag = __uint_as_float(tag_base + group_index);
