@@ -323,16 +323,17 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         // last few per cent of steady-state throughput -> the variant that defers very expensive units
         const uint32_t resident_warps = (uint32_t)s->sm_count * (uint32_t)std::max(s->ctas_per_sm_direct, 1) * CTA_WARPS;
         const uint32_t units_per_warp = (uint32_t)(((uint64_t)warps_needed * passes) / resident_warps);
-        uint32_t defer_below = 100;
+        uint32_t defer_below = 50;  // (measured with all lights in a unit: the plain variant wins a rank's quarter of the C3 frame -- 74 -- the deferring one its eighth -- 37)
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
         // Soft shadows: how many lights a unit takes in a row.  The deferring variant works per light (its units are
-        // small on purpose); everywhere else a unit lights its 32 samples with ALL lights, the running sums staying in
-        // registers -- no chained records, no waits, a fifth of the unit bookkeeping (measured: profiles/README.md).
-        // RT_LIGHTS_PER_UNIT (A/B runs, tests) selects anything in between; groups of lights are then chained as before.
+        // small on purpose); everywhere else a unit lights its 32 samples with up to 8 lights in a row -- all lights of
+        // every shipped scene --, the running sums staying in registers: no chained records, no waits, a fifth of the
+        // unit bookkeeping (measured: profiles/README.md).  A scene with more lights is lit in groups of 8, chained
+        // through the windowed records; RT_LIGHTS_PER_UNIT (A/B runs, tests) selects any other group size.
         uint32_t lights_per_unit = 1;
         if (pd.M > 1 && !defer && n_groups > 0) {
-            lights_per_unit = n_groups;
+            lights_per_unit = std::min(n_groups, 8u);
             if (const char *e = getenv("RT_LIGHTS_PER_UNIT")) lights_per_unit = (uint32_t)std::max(1, std::min<int>(atoi(e), (int)n_groups));
             n_groups = (n_groups + lights_per_unit - 1) / lights_per_unit;
             passes = n_groups;

@@ -529,16 +529,58 @@ def test_chained_records_live_in_a_bounded_window(pkg, scenes, monkeypatch, wind
     flat, dev = scenes("semesterbild", feat)
     rc = pkg.RenderConfig.from_features(feat, 2, width=384, height=320, n_light_clouds=512)   # 61440 batches of 32 samples
     monkeypatch.setenv("RT_DEFER_BELOW", "0")      # the variant that windows its records
+    ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))   # the default: all lights in one unit, nothing chained
+    monkeypatch.setenv("RT_LIGHTS_PER_UNIT", "1")  # per-light units, chained (the default before the lights moved into the unit)
     monkeypatch.setenv("RT_CHAIN_WINDOW", "1000000")   # one window
-    ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    one, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    assert np.array_equal(ref.buffer, one.buffer) and np.array_equal(ref.hit_mask, one.hit_mask)
     monkeypatch.setenv("RT_CHAIN_WINDOW", window)
     for _ in range(2):                             # (twice: the second frame finds the first one's tags in the slots)
         got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
         assert ref.hit_mask.any() and np.array_equal(ref.buffer, got.buffer) and np.array_equal(ref.hit_mask, got.hit_mask)
+    monkeypatch.setenv("RT_LIGHTS_PER_UNIT", "2")  # 5 lights in groups of 2 + 2 + 1, chained through the same windows
+    got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+    assert np.array_equal(ref.buffer, got.buffer) and np.array_equal(ref.hit_mask, got.hit_mask)
     monkeypatch.delenv("RT_CHAIN_WINDOW")
+    monkeypatch.delenv("RT_LIGHTS_PER_UNIT")
     monkeypatch.setenv("RT_DEFER_BELOW", "1000000")  # and the deferring variant right after it on the same scratch
     got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
     assert np.array_equal(ref.buffer, got.buffer)
+
+
+def test_more_lights_than_a_unit_takes(pkg, oracle_mod, monkeypatch):
+    """Soft shadows: a unit of direct_kernel lights its 32 samples with up to 8 lights in a row; a scene with more lights
+    is lit in groups of 8 chained through the windowed records.  11 lights (the 5 of semesterbild and 6 more, some behind
+    the camera, one inside the geometry): the default grouping (8 + 3), per-light units, groups of 4 and the deferring
+    variant give one image bit for bit, and that image is the oracle's."""
+    feat = "high_quality,simd_render"
+    flat = pkg.example_scene("semesterbild", feat).flatten()
+    rng = np.random.default_rng(11)
+    extra = np.zeros(6, flat.lights.dtype)
+    extra["position"] = rng.uniform(-0.2, 1.2, (6, 3)).astype(np.float32)
+    extra["color"] = rng.uniform(0.3, 1.0, (6, 3)).astype(np.float32)
+    extra["intensity"] = rng.uniform(0.1, 0.5, 6).astype(np.float32)
+    flat.lights = np.concatenate([flat.lights, extra])
+    dev = pkg.DeviceScene(flat)
+    try:
+        rc = pkg.RenderConfig.from_features(feat, 4, width=192, height=160, n_light_clouds=256)
+        monkeypatch.setenv("RT_DEFER_BELOW", "0")
+        ref, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+        assert dev.dominant_kernel_name() == "direct_kernel<false,true,false>"
+        for env in ({"RT_LIGHTS_PER_UNIT": "1"}, {"RT_LIGHTS_PER_UNIT": "4"}, {"RT_LIGHTS_PER_UNIT": "11"}, {"RT_DEFER_BELOW": "1000000"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got, _ = dev.render(rc, pkg.ImageBuffer(rc.cfg.width, rc.cfg.height))
+            assert np.array_equal(ref.buffer, got.buffer) and np.array_equal(ref.hit_mask, got.hit_mask), env
+            monkeypatch.delenv("RT_LIGHTS_PER_UNIT", raising=False)
+            monkeypatch.setenv("RT_DEFER_BELOW", "0")
+        W, H = rc.cfg.width, rc.cfg.height
+        ys, xs = np.mgrid[0:H:4, 0:W:4]
+        pix = (ys * W + xs).astype(np.uint32).ravel()
+        o_argb, o_mask, _, _ = oracle_mod.render(flat.desc(), rc.cfg, oracle_mod.BVH, 0, pix)
+        assert_image_parity(ref, o_argb, o_mask, pix)
+    finally:
+        dev.close()
 
 
 @pytest.mark.parametrize("cap", ["16384", "3000", "37", "0"])

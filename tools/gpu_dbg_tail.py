@@ -20,8 +20,8 @@ W, H = rc.cfg.width, rc.cfg.height
 slab = torch.zeros(W * H, dtype=torch.int32, device="cuda")
 mask = torch.zeros(W * H, dtype=torch.uint8, device="cuda")
 NW = 148 * 7 * 4  # (the DEFER variant runs 6 CTAs per SM: its last 592 rows stay zero)
-for world, r in ((1, 0), (8, 0)):
-    rcr = rc.with_tiles(2, r, world) if world > 1 else rc
+for world, r in ((1, 0), (8, 0), (8, 6)):
+    rcr = rc.with_tiles(8, r, world) if world > 1 else rc
     for _ in range(3):
         dev.render_device(rcr, slab.data_ptr(), mask.data_ptr(), None)
     torch.cuda.synchronize()
@@ -42,7 +42,8 @@ for world, r in ((1, 0), (8, 0)):
     print("  units / warp   :", q(units), " deferred units total", int(out[:, 7].sum()),
           "phase-B us / warp:", q(out[:, 11].astype(np.float64) / 1e3), flush=True)
     worst = out[:, 5].astype(np.float64) / 1e3
-    order = np.argsort(-worst)[:3]
+    print("  worst unit of each warp, us:", q(worst), " warps with a unit > 300 us:", int((worst > 300).sum()), " > 600 us:", int((worst > 600).sum()))
+    order = np.argsort(-worst)[:6]
     n_items = rcr.local_rows() * W * 16
     n_batches = (n_items + 31) // 32
     for w in order:

@@ -16,8 +16,10 @@ flat, rc, features, desc = bench.build_workload(name, 0)
 dev = DeviceScene(flat)
 ref = None
 for tag, env in [("default", {}), ("default again", {}), ("no deferral", {"RT_DEFER_BELOW": "0"}), ("always deferral", {"RT_DEFER_BELOW": "1000000"}),
-                 ("megakernel", {"RT_WAVEFRONT": "0"}), ("small chunks", {"RT_WAVE_CHUNK": "1048576"}), ("one window", {"RT_CHAIN_WINDOW": "100000000"})]:
-    for k in ("RT_DEFER_BELOW", "RT_WAVEFRONT", "RT_WAVE_CHUNK", "RT_CHAIN_WINDOW"):
+                 ("megakernel", {"RT_WAVEFRONT": "0"}), ("small chunks", {"RT_WAVE_CHUNK": "1048576"}),
+                 ("per-light units, one window", {"RT_LIGHTS_PER_UNIT": "1", "RT_CHAIN_WINDOW": "100000000"}),
+                 ("per-light units, windows", {"RT_LIGHTS_PER_UNIT": "1", "RT_DEFER_BELOW": "0"}), ("two lights per unit", {"RT_LIGHTS_PER_UNIT": "2", "RT_DEFER_BELOW": "0"})]:
+    for k in ("RT_DEFER_BELOW", "RT_WAVEFRONT", "RT_WAVE_CHUNK", "RT_CHAIN_WINDOW", "RT_LIGHTS_PER_UNIT"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for rep in range(2):
