@@ -399,6 +399,8 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
             pd.heavy_cap = HEAVY_CAP;
             if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
             if (const char *e = getenv("RT_DEFER_ALL")) pd.defer_all = atoi(e) != 0;  // tests: every unit asks for deferral
+            pd.defer_cand = 24;  // (B200, a rank's eighth of the C3 frame: 48 -> 1.56 ms, 32 -> 1.48, 24 -> 1.41, 16 -> 1.46, 8 -> 1.70)
+            if (const char *e = getenv("RT_DEFER_CAND")) pd.defer_cand = (uint32_t)std::max(0, atoi(e));  // A/B runs
             rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;
             CU_CHECK(cudaMemsetAsync(s->heavy_queue, 0, sizeof(HeavyQueue), stream));  // list, tickets, watchdog and the unit counter

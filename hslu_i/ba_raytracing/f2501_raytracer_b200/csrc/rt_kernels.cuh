@@ -81,6 +81,7 @@ struct RenderParams {
     uint32_t tail_div;     // 2 x warps in the grid: divisor of the guided self-scheduling
     uint32_t heavy_cap;    // direct_kernel: deferred units per launch (<= HEAVY_CAP; beyond: processed in place)
     uint32_t defer_all;    // tests only (RT_DEFER_ALL): every unit asks for deferral
+    uint32_t defer_cand;   // DEFER: a beam with more candidates than this makes its unit a heavy one (overflowed beams always do)
     uint32_t chain_window; // direct_kernel: batches per window of the chained records (see direct_kernel)
     uint32_t lights_per_unit;  // direct_kernel (soft shadows, not DEFER): lights a unit takes in a row (>= 1)
     unsigned int *chain_done;  // per batch of a window: tag of the window's last unit of that batch (slot reuse)
@@ -160,8 +161,10 @@ RT_DEV float3 copy_position(const RenderParams &p, float3 lpos, uint32_t cloud, 
 // n_cand < 0: the shadow query walks the BVH itself.
 // MODE 0: the shadow query walks the BVH itself (inlined).  MODE 1: the caller built a beam; its overflow
 // fallback (n_cand < 0) is the out-of-line traversal.  MODE 2: out-of-line traversal only.
+// Returns false when the pair adds nothing (light behind the surface or completely occluded: dc = spc = 0, and the
+// reference does not add either) -- the caller may leave its running sums alone.
 template <bool COUNT, int MODE = 0>
-RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, float3 lpos, float lint,
+RT_DEV bool shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view, float3 mcolor, float mshininess, float3 lpos, float lint,
                        float3 lcol, bool cull, Counters &cn, float3 &dc, float3 &spc, const uint32_t *cand = nullptr, int n_cand = -1,
                        int32_t *last_occluder = nullptr) {
     const DScene &sc = p.sc;
@@ -181,7 +184,7 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     const float diffuse = smax(dot3(hn, ldir), 0.0f);
     if (RT_FACING_FIRST && !(diffuse > 0.0f)) {
         if (COUNT) cn.shadow++;
-        return;
+        return false;
     }
     ShadowResult sh;
     sh.occluded = false;
@@ -216,7 +219,7 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
     }
     // Everything below only matters when the light is unoccluded AND the surface faces it
     // (`light_valid`, raytracer_renderer.rs:849): otherwise the pair adds exactly zero.
-    if (sh.occluded || !(diffuse > 0.0f)) return;
+    if (sh.occluded || !(diffuse > 0.0f)) return false;
     const float ldist = sqrt_fast(dot3(l2p, l2p)) + EPS;  // from here on: colour only (fast math, rt_device.cuh)
     const float cosn = dot3(l2p, hn);                       // cosi = cosn / ldist > 0 <=> cosn > 0 (ldist > 0)
     if (cosn > 0.0f) {  // incident_angle_pos; else colour and intensity are zero
@@ -245,6 +248,7 @@ RT_DEV void shade_pair(const RenderParams &p, float3 hp, float3 hn, float3 view,
         // specular term is l.color * (0 * opacity * spec) = 0 exactly.
         dc = mcolor * (splat(0.0f) / sh.filter) * (diffuse * 0.0f * sh.opacity);
     }
+    return true;
 }
 
 struct PathRec {  // one pending ray of a sample's reflection/refraction tree (48 B)
@@ -1352,7 +1356,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     const Beam beam = make_beam(r.P, lmin, lmax, pad);
                     n_cand = beam_collect<COUNT>(sc, beam, r.P, C - r.P, hh, cand, cn, cull ? -1.0f : p.eps_d);
                 }
-                if (DEFER) heavy = n_cand == -1;
+                if (DEFER) heavy = n_cand == -1 || n_cand > (int)p.defer_cand;  // (a long list is M long walks too)
             }
             if (DEFER && p.defer_all) heavy = true;  // (tests)
         }
@@ -1443,10 +1447,11 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                 float3 dc, spc;
                 if (!BEAM && p.M == 1) L = load_light(p, l);  // hard shadows: the group is all lights
                 const float3 lpos = p.M > 1 ? copy_position(p, L.pos, cloud, l) : L.pos;
-                shade_pair<COUNT, BEAM ? 1 : 0>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
-                                                &last_occluder);
-                sum_d = sum_d + dc;
-                sum_s = sum_s + spc;
+                if (shade_pair<COUNT, BEAM ? 1 : 0>(p, r.P, r.N, r.d, r.mcolor, r.mshininess, lpos, L.intensity, L.color, cull, cn, dc, spc, cand, n_cand,
+                                                    &last_occluder)) {
+                    sum_d = sum_d + dc;  // (x + 0 == x for every sum that can occur here: the sums start at +0 and never become -0)
+                    sum_s = sum_s + spc;
+                }
             }
         }
 #ifdef RT_DBG_TAIL
