@@ -326,13 +326,15 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         uint32_t defer_below = 50;  // (measured with all lights in a unit: the plain variant wins a rank's quarter of the C3 frame -- 74 -- the deferring one its eighth -- 37)
         if (const char *e = getenv("RT_DEFER_BELOW")) defer_below = (uint32_t)std::max(0, atoi(e));  // tuning experiments
         const bool defer = beams && units_per_warp < defer_below;
-        // Soft shadows: how many lights a unit takes in a row.  The deferring variant works per light (its units are
-        // small on purpose); everywhere else a unit lights its 32 samples with up to 8 lights in a row -- all lights of
-        // every shipped scene --, the running sums staying in registers: no chained records, no waits, a fifth of the
-        // unit bookkeeping (measured: profiles/README.md).  A scene with more lights is lit in groups of 8, chained
-        // through the windowed records; RT_LIGHTS_PER_UNIT (A/B runs, tests) selects any other group size.
+        // Soft shadows: how many lights a unit takes in a row.  A unit lights its 32 samples with up to 8 lights in a row
+        // -- all lights of every shipped scene --, the running sums staying in registers: no chained records, no waits,
+        // a fifth of the unit bookkeeping (measured: profiles/README.md).  A scene with more lights is lit in groups of
+        // 8, chained through the records; RT_LIGHTS_PER_UNIT (A/B runs, tests) selects any other group size.  The
+        // deferring variant keeps its records, tags and list entries per LIGHT whatever the unit size (a unit that defers
+        // at one of its lights goes on as the per-light units of its batch).
+        const uint32_t lights_pl = std::max(n_groups, 1u);  // per-light count (soft shadows), 1 otherwise
         uint32_t lights_per_unit = 1;
-        if (pd.M > 1 && !defer && n_groups > 0) {
+        if (pd.M > 1 && n_groups > 0) {
             lights_per_unit = std::min(n_groups, 8u);
             if (const char *e = getenv("RT_LIGHTS_PER_UNIT")) lights_per_unit = (uint32_t)std::max(1, std::min<int>(atoi(e), (int)n_groups));
             n_groups = (n_groups + lights_per_unit - 1) / lights_per_unit;
@@ -350,10 +352,10 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
         chain_window = std::max(chain_window, 2u * resident_warps);  // (below: one working warp per batch column, the rest waiting)
         chain_window = defer ? warps_needed : std::min(chain_window, warps_needed);
         const uint32_t n_windows = (warps_needed + chain_window - 1) / chain_window;
-        const uint32_t gens = passes > 1 ? (defer ? passes - 1 : std::min(2u, passes - 1)) : 1u;
+        const uint32_t gens = defer ? std::max(lights_pl, 2u) - 1 : passes > 1 ? std::min(2u, passes - 1) : 1u;
         {
             const size_t before = s->direct_cap, before_done = s->chain_done_cap;
-            const size_t n_records = passes > 1 ? (size_t)chain_window * 32 * gens : 1;  // (one group: nothing is chained)
+            const size_t n_records = (defer ? lights_pl > 1 : passes > 1) ? (size_t)chain_window * 32 * gens : 1;  // (one group: nothing is chained)
             rc = grow(s->direct_state, s->direct_cap, n_records * sizeof(DirectState));
             if (rc) return rc;
             if ((rc = grow(s->chain_done, s->chain_done_cap, (size_t)chain_window * sizeof(unsigned int)))) return rc;
@@ -361,7 +363,7 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
             if (s->chain_done_cap != before_done) CU_CHECK(cudaMemsetAsync(s->chain_done, 0, s->chain_done_cap, stream));
         }
         // tags of this frame's chained records, one per (window, group): never equal to a tag an earlier frame left behind
-        const uint64_t tags = (uint64_t)n_windows * passes + 1;
+        const uint64_t tags = (defer ? (uint64_t)lights_pl : (uint64_t)n_windows * passes) + 1;
         if (tags >= 0x7FFF0000ull) return rt_fail(RT_ERR_INVALID_ARGUMENT, "frame too large for one call (%llu chain tags)", (unsigned long long)tags);
         if (s->frame_serial == 0 || (uint64_t)s->frame_serial + tags > 0x7FFF0000ull) {  // (the top bit of a chain tag is CHAIN_DEFERRED)
             CU_CHECK(cudaMemsetAsync(s->direct_state, 0, s->direct_cap, stream));
@@ -399,7 +401,7 @@ static int enqueue_direct_lighting(rt_scene *s, const rt_config *cfg, const Rend
             pd.heavy_cap = HEAVY_CAP;
             if (const char *e = getenv("RT_HEAVY_CAP")) pd.heavy_cap = (uint32_t)std::min<long>(HEAVY_CAP, std::max<long>(0, atol(e)));  // tests: the list-full path
             if (const char *e = getenv("RT_DEFER_ALL")) pd.defer_all = atoi(e) != 0;  // tests: every unit asks for deferral
-            pd.defer_cand = 24;  // (B200, a rank's eighth of the C3 frame: 48 -> 1.56 ms, 32 -> 1.48, 24 -> 1.41, 16 -> 1.46, 8 -> 1.70)
+            pd.defer_cand = 32;  // (B200, a rank's eighth of the C3 frame, max over the 8 ranks: 48 -> 1.56 ms, 32 -> 1.38, 24 -> 1.42, 16 -> 1.50)
             if (const char *e = getenv("RT_DEFER_CAND")) pd.defer_cand = (uint32_t)std::max(0, atoi(e));  // A/B runs
             rc = grow(s->heavy_scratch, s->heavy_scratch_cap, (size_t)HEAVY_CAP * pd.M * 32 * 2 * sizeof(float4));
             if (rc) return rc;

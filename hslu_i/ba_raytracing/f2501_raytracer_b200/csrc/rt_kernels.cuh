@@ -1240,7 +1240,10 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
     const uint32_t n_batches = (p.n_items + 31u) / 32u;
     const uint32_t n_units = n_batches * n_groups;
     const uint32_t window = DEFER ? n_batches : p.chain_window;  // batches per window (>= 1)
-    const uint32_t lpu = (!DEFER && p.M > 1) ? p.lights_per_unit : 1u;  // lights per unit (soft shadows); DEFER: a unit is one light
+    const uint32_t lpu = p.M > 1 ? p.lights_per_unit : 1u;  // lights a unit takes in a row (soft shadows)
+    // DEFER keeps its records, tags and list entries PER LIGHT whatever the unit size: a unit that defers at its light g
+    // becomes, from there on, the per-light units g, g+1, .. of its batch (below)
+    const uint32_t n_lights_pl = p.M > 1 ? sc.n_lights : 1u;
     const uint32_t window_units = window * n_groups;
     const size_t chain_stride = (size_t)window * 32u;  // records of one generation
     const bool deferring = DEFER && BEAM && hq != nullptr;
@@ -1269,11 +1272,13 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         const bool last = group_index + 1 == n_groups;
         const uint32_t item = batch * 32u + lane;
         const SampleRec r = rebuild_sample<POINTS>(p, item);
-        // generation of a record: the group itself (DEFER: one window, every generation kept) or its parity
-        const uint32_t gen = DEFER ? group_index : (group_index & 1u), prev_gen = DEFER ? group_index - 1u : (gen ^ 1u);
+        // generation of a record: the parity of the group, or (DEFER: one window, every generation kept) the LIGHT the
+        // sums stand after -- the unit's last light for its own record, the light before its first one for the predecessor's
+        const uint32_t first_light = group_index * lpu, last_light = min(first_light + lpu, n_lights_pl) - 1u;  // (DEFER)
+        const uint32_t gen = DEFER ? last_light : (group_index & 1u), prev_gen = DEFER ? first_light - 1u : (gen ^ 1u);
         DirectState *const own_rec = state + (size_t)gen * chain_stride + (size_t)b_in_win * 32u + lane;
         const DirectState *const prev_rec = state + (size_t)prev_gen * chain_stride + (size_t)b_in_win * 32u + lane;  // (only dereferenced when group_index > 0)
-        const uint32_t tag_base = frame_tag + win * n_groups;  // tags are unique per (frame, window, group)
+        const uint32_t tag_base = frame_tag + win * n_groups;  // tags are unique per (frame, window, group); DEFER: frame_tag + light
         if (!DEFER && win > 0 && (group_index == 0 || last) && n_groups > 1) {
             // The FIRST unit of a batch column in a window: its records reuse the slots of the previous window -- wait
             // until that window's last unit of this column, and with it (through the chain) every reader of those slots,
@@ -1303,7 +1308,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         if (r.hit) {
             if (group_index > 0) {
                 // wait for (this sample, previous group): gpu-scope loads see the producer's stores in L2
-                const uint32_t want = tag_base + group_index - 1u;
+                const uint32_t want = DEFER ? frame_tag + first_light - 1u : tag_base + group_index - 1u;
                 float4 sd, ss;
 #ifdef RT_DBG_TAIL
                 const unsigned long long dbg_s0 = dbg_globaltimer();
@@ -1365,16 +1370,19 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
             const unsigned heavy_lanes = __ballot_sync(FULL, heavy), inherit = __ballot_sync(FULL, inherited_slot != 0xFFFFFFFFu);
             if (heavy_lanes | inherit) {
                 // A unit never waits for a listed predecessor: either it inherits the slot that was reserved for it when
-                // the first unit of its chain was listed, or (fresh: one of its beams overflowed) it reserves slots for
-                // itself AND every later group of this batch at once -- all or nothing, so the list never holds a unit
-                // whose successors cannot follow it.  No room: processed in place (its predecessor is then not on the
-                // list: nothing to wait for).
+                // the first light of its chain was listed, or (fresh: one of its beams is a heavy one) it reserves slots
+                // for this light AND every later light of its batch at once -- all or nothing, so the list never holds a
+                // light whose successors cannot follow it.  No room: processed in place (its predecessor is then not on
+                // the list: nothing to wait for).  From the light it defers at, a unit of several lights goes on as the
+                // per-light units of its batch would: every later light inherits the next slot.
+                const bool last_l = li0 + 1u == n_lights_pl;
+                DirectState *const rec_l = state + (size_t)li0 * chain_stride + (size_t)b_in_win * 32u + lane;  // (DEFER: generation = light)
                 unsigned int idx = 0xFFFFFFFFu;
                 if (inherit) {
                     idx = __shfl_sync(FULL, inherited_slot, __ffs(inherit) - 1);
                 } else {
                     if (lane == 0) {
-                        const unsigned int k = n_groups - group_index;
+                        const unsigned int k = n_lights_pl - li0;
                         unsigned int old = ld_volatile_u32(&hq->n_heavy);
                         for (;;) {
                             if (old + k > p.heavy_cap) break;
@@ -1387,28 +1395,36 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                         }
                     }
                     idx = __shfl_sync(FULL, idx, 0);
+                    if (idx != 0xFFFFFFFFu && gl > 0 && r.hit) {
+                        // deferred in the middle of the unit: the sums so far are the record the list continues from
+                        const float tag = __uint_as_float(frame_tag + li0 - 1u);
+                        DirectState *const before = rec_l - chain_stride;
+                        st_relaxed_gpu(&before->d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
+                        st_relaxed_gpu(&before->s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
+                    }
                 }
                 if (idx != 0xFFFFFFFFu && heavy_lanes) {
                     // very expensive: worked off as M sub-tasks by all warps once the unit queue is dry
-                    defer_unit(hq, own_rec, p.samples + r.sample_index, unit, idx, (tag_base + group_index) | CHAIN_DEFERRED, !last && r.hit,
-                               last && r.valid && !r.hit);
+                    defer_unit(hq, rec_l, p.samples + r.sample_index, li0 * n_batches + batch, idx, (frame_tag + li0) | CHAIN_DEFERRED, !last_l && r.hit,
+                               last_l && r.valid && !r.hit);
 #ifdef RT_DBG_TAIL
                     dbg_helped++;
 #endif
                     unit_parked = true;
-                    break;
+                    inherited_slot = idx + 1u;  // (the unit's next light, if any)
+                    continue;
                 }
                 if (idx != 0xFFFFFFFFu) {
-                    // Only its predecessor is listed, the unit itself is an ordinary one: its M contributions are computed
-                    // here and now, through the beams like any other unit's, and parked in the slot's scratch slab; what
+                    // Only its predecessor is listed, the light itself is an ordinary one: its M contributions are computed
+                    // here and now, through the beams like any other's, and parked in the slot's scratch slab; what
                     // waits for the predecessor is just the M ordered additions (finish_chain).  (Before: all M x 32 rays of
                     // such a unit were traced again by BVH walks as sub-tasks -- most of the work of the final phase.)
-                    if (!last && r.hit) {  // successors must not wait for the record either
-                        const float tag = __uint_as_float((tag_base + group_index) | CHAIN_DEFERRED);
-                        st_relaxed_gpu(&own_rec->d, make_float4(__uint_as_float(idx), 0.0f, 0.0f, tag));
-                        st_relaxed_gpu(&own_rec->s, make_float4(0.0f, 0.0f, 0.0f, tag));
+                    if (!last_l && r.hit) {  // successors must not wait for the record either
+                        const float tag = __uint_as_float((frame_tag + li0) | CHAIN_DEFERRED);
+                        st_relaxed_gpu(&rec_l->d, make_float4(__uint_as_float(idx), 0.0f, 0.0f, tag));
+                        st_relaxed_gpu(&rec_l->s, make_float4(0.0f, 0.0f, 0.0f, tag));
                     }
-                    if (last && r.valid && !r.hit) p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (last_l && r.valid && !r.hit) p.samples[r.sample_index] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if (r.hit) {
                         float4 *slab = hscratch + ((size_t)idx * p.M * 32u + lane) * 2u;  // + copy * 64
                         if (COUNT && n_cand == BEAM_COVERED) cn.shadow += n_in_group;
@@ -1425,9 +1441,10 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
                     __syncwarp();
                     if (lane == 0) atomicAdd(&hq->done[idx], p.M);  // all M contributions at once
                     __threadfence();
-                    finish_chain<POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, idx, group_index, batch);
+                    finish_chain<POINTS>(gp, hq, hscratch, state, n_lights_pl, frame_tag, idx, li0, batch);
                     unit_parked = true;
-                    break;
+                    inherited_slot = idx + 1u;
+                    continue;
                 }
             }
         }
@@ -1470,7 +1487,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
         if (DEFER && unit_parked) continue;
         if (r.hit) {
             if (!last) {
-                const float tag = __uint_as_float(tag_base + group_index);
+                const float tag = __uint_as_float(DEFER ? frame_tag + last_light : tag_base + group_index);
                 st_relaxed_gpu(&own_rec->d, make_float4(sum_d.x, sum_d.y, sum_d.z, tag));
                 st_relaxed_gpu(&own_rec->s, make_float4(sum_s.x, sum_s.y, sum_s.z, tag));
             } else {
@@ -1491,7 +1508,7 @@ __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT
 #ifdef RT_DBG_TAIL
         const unsigned long long dbg_h0 = dbg_globaltimer();
 #endif
-        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_groups, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
+        finish_heavy_units<COUNT, POINTS>(gp, hq, hscratch, state, n_lights_pl, frame_tag, gridDim.x * (blockDim.x >> 5), COUNT ? &cn : nullptr, watchdog);
 #ifdef RT_DBG_TAIL
         dbg_help_time += dbg_globaltimer() - dbg_h0;
 #endif
