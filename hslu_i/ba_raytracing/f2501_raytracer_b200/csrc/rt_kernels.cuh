@@ -1225,7 +1225,7 @@ __device__ __noinline__ void defer_unit(HeavyQueue *hq, DirectState *own_rec, fl
 #define RT_WAIT_BACKOFF_NS 200  // sleep between two polls of a chained record that is not there yet (0: plain polling)
 #endif
 #ifndef RT_DEFER_MIN_CTAS
-#define RT_DEFER_MIN_CTAS 6  // the DEFER variant is better off with 80 registers (measured: -2.3 % on a rank's eighth of C3)
+#define RT_DEFER_MIN_CTAS 7  // (B200, units of all lights: a rank's eighth of C3 takes 1.38 ms with 5, 6 or 7 CTAs per SM; the full frame 10.11 / 10.02 / 9.78 ms)
 #endif
 template <bool COUNT, bool BEAM, bool DEFER, bool POINTS = false>
 __global__ void __launch_bounds__(RT_CTA_THREADS, DEFER ? RT_DEFER_MIN_CTAS : RT_DIRECT_MIN_CTAS) direct_kernel(const RenderParams p, uint32_t n_groups, uint32_t frame_tag,
