@@ -45,10 +45,11 @@ def _build_emu(lib_name, defines=()):
 @pytest.fixture(scope="module", params=["product", "round1_filter"])
 def emu(request):
     """"product": the device code as the product builds it (beam-filter switches RT_SPHERE_MISS_CULL / RT_SELF_CULL on).
-    "round1_filter": the same code with both switches off (the round-1 filter), which stays buildable for A/B runs."""
+    "round1_filter": the same code with both switches off (the round-1 filter) and the BVH walks in their node-or-leaf
+    form (RT_WW_* = 0; the product's walks descend to a leaf first), which stays buildable for A/B runs."""
     if request.param == "product":
         return _build_emu("libdevice_emu.so")
-    return _build_emu("libdevice_emu_r1.so", ("-DRT_SPHERE_MISS_CULL=0", "-DRT_SELF_CULL=0"))
+    return _build_emu("libdevice_emu_r1.so", ("-DRT_SPHERE_MISS_CULL=0", "-DRT_SELF_CULL=0", "-DRT_WW_CLOSEST=0", "-DRT_WW_SHADOW_INLINE=0"))
 
 
 def ptr(a):
