@@ -134,6 +134,7 @@ def oracle_sample(flat, rc, n_pixels: int, threads: int, seed: int = 1234):
     t0 = time.perf_counter()
     _, _, _, cnt = oracle.render(desc, rc.cfg, oracle.PACKET8, threads, pix)
     dt = time.perf_counter() - t0
+    oracle_sample.last_counters = cnt  # (cpu_baseline reports the share of shadow queries whose surface faces away from the light)
     return cnt["closest_rays"] + cnt["shadow_rays"], dt, len(pix)
 
 
@@ -155,7 +156,12 @@ def cpu_baseline(flat, rc, budget_s: float = 15.0) -> dict:
     cores = os.cpu_count() or 1
     n = size_sample(flat, rc, cores, budget_s)
     rays, dt, n = oracle_sample(flat, rc, n, cores)
+    cnt = oracle_sample.last_counters
     return {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "shadow_queries_facing_away": {
+                "fraction": cnt["shadow_rays_facing_away"] / max(cnt["shadow_rays"], 1),
+                "note": "share of the sample's shadow queries whose hit faces away from the light (`light_valid` false, raytracer_renderer.rs:849): the "
+                        "reference casts them and drops the result, the CUDA path decides `diffuse > 0` first and traces nothing; both arms count them as rays"},
             "sample": f"{n} random pixels of the workload ({rays} rays, {dt:.1f} s), brute-force C++ oracle, "
                       f"8-ray AVX2 packets (the reference's simd_render instantiation: linear scan over all {flat.n_primitives} "
                       f"primitives per packet), {cores} threads, pixel queue in chunks of {max(1, min(64, n // (8 * cores)))}"}

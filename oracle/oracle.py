@@ -52,14 +52,14 @@ def render(desc, cfg, mode: int = BVH, threads: int = 0, pixels: np.ndarray | No
     argb = np.zeros(n, np.uint32)
     mask = np.zeros(n, np.uint8)
     rgb = np.zeros((n, 3), np.float32) if want_rgb else None
-    cnt = np.zeros(5, np.uint64)
+    cnt = np.zeros(6, np.uint64)
     pix = None if pixels is None else np.ascontiguousarray(pixels, np.uint32)
     rc = lib.oracle_render(C.addressof(desc), C.addressof(cfg), mode, threads,
                            None if pix is None else pix.ctypes.data, 0 if pix is None else len(pix),
                            argb.ctypes.data, mask.ctypes.data, None if rgb is None else rgb.ctypes.data, cnt.ctypes.data)
     if rc:
         raise RuntimeError(f"oracle_render failed: {rc}")
-    counters = dict(zip(["closest_rays", "shadow_rays", "triangle_tests", "sphere_tests", "box_tests"], map(int, cnt)))
+    counters = dict(zip(["closest_rays", "shadow_rays", "triangle_tests", "sphere_tests", "box_tests", "shadow_rays_facing_away"], map(int, cnt)))
     return argb, mask, rgb, counters
 
 

@@ -170,6 +170,7 @@ struct Hit {  // SurfaceInteraction<Vec3> (src/raytracing/surface_interaction.rs
 
 struct Counters {
     uint64_t closest = 0, shadow = 0, tri = 0, sph = 0, box = 0;
+    uint64_t facing_away = 0;  // shadow queries of a hit whose surface faces away from the light (`light_valid` false: the pair adds nothing)
 };
 
 struct BvhNode {
@@ -748,6 +749,7 @@ struct Renderer {
             V3 light_dir = normalized(light_to_point);
             V3 check_point = it.p + light_dir * k.eps_d;
             V3 check_l2p = l.pos - check_point;
+            if (!(smax(dot(it.n, light_dir), 0.0f) > 0.0f)) tr.cn.facing_away++;  // (statistics only: the query is made all the same)
             Shadow sh = tr.has_any_intersection(check_point, light_dir, mag(check_l2p));
             if (sh.occluded) continue;
             // PointLight::calculate_contribution_at
@@ -888,6 +890,8 @@ struct Renderer {
             }
             Shadow sh[8];
             tr.has_any_intersection8(from, dirs, maxd, sh);
+            for (int l = 0; l < 8; l++)
+                if (hit[l].valid && !(smax(dot(hit[l].n, ldir[l]), 0.0f) > 0.0f)) tr.cn.facing_away++;  // (statistics only)
             for (int l = 0; l < 8; l++) {
                 if (!hit[l].valid || sh[l].occluded) continue;
                 const Mat &m = sc.mats[hit[l].mat];
@@ -1082,7 +1086,8 @@ int oracle_version(void) { return 1; }
 
 // Renders either the whole frame (pixel_idx == NULL; row tiles honoured) or the listed pixels.
 // out_argb/out_mask are width*height (zero-filled here; misses stay 0). out_rgb (optional) is
-// width*height*3 floats. counters[5] = closest rays, shadow rays, triangle tests, sphere tests, box tests.
+// width*height*3 floats. counters[6] = closest rays, shadow rays, triangle tests, sphere tests, box tests, shadow
+// queries of hits that face away from the light.
 int oracle_render(const OSceneDesc *desc, const OConfig *cfg, int mode, int threads, const uint32_t *pixel_idx,
                   uint32_t n_pixels, uint32_t *out_argb, uint8_t *out_mask, float *out_rgb, uint64_t *counters) {
     if (!desc || !cfg || !out_argb) return -1;
@@ -1138,13 +1143,14 @@ int oracle_render(const OSceneDesc *desc, const OConfig *cfg, int mode, int thre
     work(0);
     for (auto &t : th) t.join();
     if (counters) {
-        memset(counters, 0, 5 * sizeof(uint64_t));
+        memset(counters, 0, 6 * sizeof(uint64_t));
         for (auto &c : cns) {
             counters[0] += c.closest;
             counters[1] += c.shadow;
             counters[2] += c.tri;
             counters[3] += c.sph;
             counters[4] += c.box;
+            counters[5] += c.facing_away;
         }
     }
     return 0;
