@@ -4,12 +4,12 @@ mkdir -p gpurun_out
 {
 for lpu in 1 2 3 5; do
   echo "RT_LIGHTS_PER_UNIT=$lpu"
-  RT_LIGHTS_PER_UNIT=$lpu timeout 300 python build/bisect/probe.py . c3 28 2>&1 | tail -n 1
+  RT_LIGHTS_PER_UNIT=$lpu timeout 300 python tools/gpu_probe.py . c3 28 2>&1 | tail -n 1
 done
 for w in c1 c4 c5; do
   for lpu in 1 99; do
     echo "RT_LIGHTS_PER_UNIT=$lpu"
-    RT_LIGHTS_PER_UNIT=$lpu timeout 600 python build/bisect/probe.py . $w 8 2>&1 | tail -n 1
+    RT_LIGHTS_PER_UNIT=$lpu timeout 600 python tools/gpu_probe.py . $w 8 2>&1 | tail -n 1
   done
 done
 } > gpurun_out/r2c16_ab.txt 2>&1

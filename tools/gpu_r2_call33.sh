@@ -5,9 +5,9 @@ mkdir -p gpurun_out
 for lib in "" build/librt_wwB.so build/librt_wwC.so; do
   echo "== lib=${lib:-product (A)}"
   export RT_LIB_PATH=${lib:-hslu_i/ba_raytracing/f2501_raytracer_b200/librt_b200.so}
-  timeout 200 python build/bisect/probe.py . c4 40 2>&1 | tail -n 1
-  timeout 200 python build/bisect/probe.py . c2 40 2>&1 | tail -n 1
-  timeout 200 python build/bisect/probe.py . c3 14 2>&1 | tail -n 1
+  timeout 200 python tools/gpu_probe.py . c4 40 2>&1 | tail -n 1
+  timeout 200 python tools/gpu_probe.py . c2 40 2>&1 | tail -n 1
+  timeout 200 python tools/gpu_probe.py . c3 14 2>&1 | tail -n 1
   timeout 200 python tools/gpu_tiles_onegpu.py 8 2 2>&1 | grep world | cut -c1-110
 done
 } > gpurun_out/r2c33_ab.txt 2>&1
